@@ -1,0 +1,468 @@
+// Flash-attention backward on tcgen05 (backward of models/transformer.py:53-63, reached from engine/engine.py:120).
+//
+// One CTA per (128-key tile j, head, batch), looping over the query tiles i >= j that can see it. 160 threads:
+//   warps 0..3  compute: thread r owns key row r of the transposed score tile (TMEM lane r)
+//   warp 4      control: one thread issues TMA (K,V once; Q_i,dO_i double-buffered) and all tcgen05.mma
+// Five GEMMs per (j, i) pair, all on the tensor core with TMEM accumulators (448 of 512 columns):
+//   S^T  = K Q_i^T        (cols   0..127)      dP^T = V dO_i^T       (cols 128..255)
+//   dV  += P^T dO_i       (cols 256..319)      dK  += dS^T Q_i       (cols 320..383)
+//   dQ_i = dS K           (cols 384..447) -> fp32 red.add into dq_acc (finalised by dq_finalize_kernel)
+// P^T and dS^T are written once to swizzled smem as K-major A operands; the SAME dS^T buffer is re-read as an
+// MN-major A operand for the dQ GEMM, and Q_i / dO_i / K are consumed as MN-major B operands straight from their TMA
+// boxes — no transposes anywhere.  dK and dQ are rotated back through RoPE in the epilogues.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <mutex>
+
+namespace plm {
+
+constexpr int AB_T = 128;   // tile edge (keys per CTA, queries per step)
+constexpr int AB_HD = 64;
+constexpr int AB_THREADS = 160;
+constexpr int AB_TILE = AB_T * AB_HD * 2;  // 16 KB
+// K, V, (Q,dO) x2, P^T (2 blocks), dS^T (2 blocks), vectors (lse2, delta, seg) x2 stages, barriers
+constexpr int AB_VEC_BYTES = 2 * 3 * AB_T * 4;
+constexpr int AB_SMEM = AB_TILE * (2 + 4 + 2 + 2) + AB_VEC_BYTES + 128;
+
+__device__ __forceinline__ float ex2b(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// delta[b,h,t] = sum_c dO[t,h,c] * O[t,h,c].  8 lanes per (row, head): each lane 8 elements.
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const uint4* __restrict__ o, const uint4* __restrict__ dout, float* __restrict__ delta, int64_t rows,
+                  int T, int H) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // one per 8 elements
+  const int64_t total = rows * H * 8;
+  float s = 0.f;
+  if (idx < total) {
+    const uint4 a = __ldg(o + idx), g = __ldg(dout + idx);
+    s = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
+        bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
+        bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  if (idx < total && (threadIdx.x & 7) == 0) {
+    const int64_t rh = idx >> 3;  // row * H + h
+    const int64_t row = rh / H;
+    const int h = static_cast<int>(rh - row * H);
+    const int64_t b = row / T;
+    const int t = static_cast<int>(row - b * T);
+    delta[(b * H + h) * T + t] = s;
+  }
+}
+
+// dq_acc fp32 [rows, d] -> inverse RoPE -> bf16 into dqkv[:, 0:d].  One thread per 8 columns.
+__global__ void __launch_bounds__(256)
+dq_finalize_kernel(const float* __restrict__ dq_acc, const float* __restrict__ table, __nv_bfloat16* __restrict__ dqkv,
+                   int64_t rows, int T, int d, int hd) {
+  const int d8 = d >> 3;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= rows * d8) return;
+  const int64_t r = idx / d8;
+  const int c = static_cast<int>(idx - r * d8) * 8;
+  const float4 a = __ldcs(reinterpret_cast<const float4*>(dq_acc + r * d + c));
+  const float4 b = __ldcs(reinterpret_cast<const float4*>(dq_acc + r * d + c) + 1);
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (table) {
+    const int pos = static_cast<int>(r % T);
+    const int pair0 = (c % hd) >> 1;
+    const float4* tab = reinterpret_cast<const float4*>(table + (static_cast<int64_t>(pos) * (hd >> 1) + pair0) * 2);
+    const float4 cs0 = __ldg(tab), cs1 = __ldg(tab + 1);
+    const float cosv[4] = {cs0.x, cs0.z, cs1.x, cs1.z};
+    const float sinv[4] = {cs0.y, cs0.w, cs1.y, cs1.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // transpose of the forward rotation = rotation by -theta
+      const float x0 = v[2 * i], x1 = v[2 * i + 1];
+      v[2 * i] = x0 * cosv[i] + x1 * sinv[i];
+      v[2 * i + 1] = x1 * cosv[i] - x0 * sinv[i];
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]);
+  o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]);
+  o.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(dqkv + r * (3 * d) + c) = o;
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const float* __restrict__ lse, const float* __restrict__ delta, const int32_t* __restrict__ seg_start,
+                const float* __restrict__ rope, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_acc, int T,
+                int H, float scale, float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + AB_TILE;
+  uint8_t* sQ = smem + 2 * AB_TILE;    // [2]
+  uint8_t* sDO = smem + 4 * AB_TILE;   // [2]
+  uint8_t* sP = smem + 6 * AB_TILE;    // P^T : 2 blocks (q 0..63 | 64..127), each [128 kv rows x 128 B]
+  uint8_t* sDS = smem + 8 * AB_TILE;   // dS^T: same layout
+  float* sLse = reinterpret_cast<float*>(smem + 10 * AB_TILE);  // [2][128]  lse * log2(e)
+  float* sDelta = sLse + 2 * AB_T;                               // [2][128]
+  int32_t* sSeg = reinterpret_cast<int32_t*>(sDelta + 2 * AB_T); // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * AB_TILE + AB_VEC_BYTES);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;   // [2]
+  uint64_t* qdo_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* dp_full = bars + 6;
+  uint64_t* pds_full = bars + 7;
+  uint64_t* dq_full = bars + 8;
+  uint64_t* dq_empty = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  if ((smem_u32(smem) & 1023u) != 0) return;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nq = T / AB_T;
+  const int j = blockIdx.x;  // key tile
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int d = H * AB_HD;
+  const int64_t seq0 = static_cast<int64_t>(b) * T;
+  const int64_t krow0 = seq0 + j * AB_T;
+
+  // last query tile that can see this key tile: seg_start is non-decreasing in t
+  int i_hi = nq - 1;
+  if (seg_start) {
+    const int k_last = j * AB_T + AB_T - 1;
+    while (i_hi > j && seg_start[seq0 + i_hi * AB_T] > k_last) --i_hi;
+  }
+  const int n_it = i_hi - j + 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&qdo_full[s], 1);
+      mbar_init(&qdo_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(pds_full, 4);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc<512>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
+                 tDQ = tmem_base + 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ control thread
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // K-major x K-major, N = 128 queries
+      constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);   // A K-major, B MN-major, N = 64 (dV, dK)
+      constexpr uint32_t idesc_nn = make_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major (dQ)
+      mbar_arrive_expect_tx(kv_full, 2 * AB_TILE);
+      tma_load_2d(sK, &tmQKV, kv_full, d + h * AB_HD, static_cast<int>(krow0));
+      tma_load_2d(sV, &tmQKV, kv_full, 2 * d + h * AB_HD, static_cast<int>(krow0));
+      {
+        const int qr = static_cast<int>(seq0 + j * AB_T);
+        mbar_arrive_expect_tx(&qdo_full[0], 2 * AB_TILE);
+        tma_load_2d(sQ, &tmQKV, &qdo_full[0], h * AB_HD, qr);
+        tma_load_2d(sDO, &tmDO, &qdo_full[0], h * AB_HD, qr);
+      }
+      mbar_wait(kv_full, 0);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        const uint32_t q_addr = smem_u32(sQ + st * AB_TILE), do_addr = smem_u32(sDO + st * AB_TILE);
+        mbar_wait(&qdo_full[st], (it >> 1) & 1);
+        tc_fence_after();
+        // S^T = K Q^T ; dP^T = V dO^T      (TMEM regions are free: pds_full(it-1) was awaited below)
+#pragma unroll
+        for (int k = 0; k < AB_HD / 16; ++k)
+          umma_ss(tS, make_smem_desc_sw128(k_addr + k * 32, 16, 1024), make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
+                  idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+#pragma unroll
+        for (int k = 0; k < AB_HD / 16; ++k)
+          umma_ss(tDP, make_smem_desc_sw128(v_addr + k * 32, 16, 1024),
+                  make_smem_desc_sw128(do_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(dp_full);
+        // prefetch next Q / dO
+        if (it + 1 < n_it) {
+          const int nst = (it + 1) & 1;
+          mbar_wait(&qdo_empty[nst], (((it + 1) >> 1) & 1) ^ 1);
+          const int qr = static_cast<int>(seq0 + (j + it + 1) * AB_T);
+          mbar_arrive_expect_tx(&qdo_full[nst], 2 * AB_TILE);
+          tma_load_2d(sQ + nst * AB_TILE, &tmQKV, &qdo_full[nst], h * AB_HD, qr);
+          tma_load_2d(sDO + nst * AB_TILE, &tmDO, &qdo_full[nst], h * AB_HD, qr);
+        }
+        mbar_wait(pds_full, it & 1);
+        tc_fence_after();
+        // dV += P^T dO ; dK += dS^T Q      (reduction over the 128 queries of this step)
+#pragma unroll
+        for (int k = 0; k < AB_T / 16; ++k)
+          umma_ss(tDV, make_smem_desc_sw128(p_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 16, 1024),
+                  make_smem_desc_sw128(do_addr + k * 2048, AB_TILE, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < AB_T / 16; ++k)
+          umma_ss(tDK, make_smem_desc_sw128(ds_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 16, 1024),
+                  make_smem_desc_sw128(q_addr + k * 2048, AB_TILE, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
+        // dQ = dS K : A = dS^T buffer read MN-major (M = queries, 64 per block, blocks AB_TILE apart), B = K MN-major
+        if (it > 0) {
+          mbar_wait(dq_empty, (it - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int k = 0; k < AB_T / 16; ++k)
+          umma_ss(tDQ, make_smem_desc_sw128(ds_addr + k * 2048, AB_TILE, 1024),
+                  make_smem_desc_sw128(k_addr + k * 2048, AB_TILE, 1024), idesc_nn, k > 0 ? 1u : 0u);
+        umma_commit(&qdo_empty[st]);
+        umma_commit(dq_full);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ compute warps
+    const int r = warp * 32 + lane;  // key row within the tile (S^T lane) / query row within the tile (dQ lane)
+    const int kj = j * AB_T + r;     // key position
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+
+    for (int it = 0; it < n_it; ++it) {
+      const int i = j + it;
+      const int st = it & 1;
+      // stage the per-query vectors of this step
+      {
+        const int64_t qrow = seq0 + i * AB_T + r;
+        const int64_t vidx = (static_cast<int64_t>(b) * H + h) * T + i * AB_T + r;
+        sLse[st * AB_T + r] = lse[vidx] * 1.4426950408889634f;
+        sDelta[st * AB_T + r] = delta[vidx];
+        sSeg[st * AB_T + r] = seg_start ? seg_start[qrow] : 0;
+      }
+      named_bar_sync(1, 128);
+      const float* lse2 = sLse + st * AB_T;
+      const float* dl = sDelta + st * AB_T;
+      const int32_t* sg = sSeg + st * AB_T;
+      const int qbase = i * AB_T;
+
+      // previous step's dV/dK/dQ MMAs must have finished reading the P^T / dS^T buffers
+      if (it > 0) {
+        mbar_wait(dq_full, (it - 1) & 1);
+        tc_fence_after();
+      }
+
+      // ---- P^T
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      float p[AB_T];
+#pragma unroll
+      for (int c = 0; c < AB_T / 32; ++c) {
+        uint32_t t[32];
+        tmem_ld32(tS + lane_off + c * 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int qq = c * 32 + q;
+          const int qi = qbase + qq;
+          const bool ok = (kj <= qi) && (kj >= sg[qq]);
+          p[qq] = ok ? ex2b(__uint_as_float(t[q]) * scale_log2 - lse2[qq]) : 0.f;
+        }
+      }
+      uint8_t* prow = sP + r * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < AB_T / 8; ++c16) {
+        uint4 v;
+        v.x = pack_bf16x2(p[c16 * 8 + 0], p[c16 * 8 + 1]);
+        v.y = pack_bf16x2(p[c16 * 8 + 2], p[c16 * 8 + 3]);
+        v.z = pack_bf16x2(p[c16 * 8 + 4], p[c16 * 8 + 5]);
+        v.w = pack_bf16x2(p[c16 * 8 + 6], p[c16 * 8 + 7]);
+        *reinterpret_cast<uint4*>(prow + (c16 >> 3) * AB_TILE + (((c16 & 7) ^ (r & 7)) << 4)) = v;
+      }
+      // ---- dS^T = P^T o (dP^T - delta) * scale
+      mbar_wait(dp_full, it & 1);
+      tc_fence_after();
+      uint8_t* dsrow = sDS + r * 128;
+#pragma unroll
+      for (int c = 0; c < AB_T / 32; ++c) {
+        uint32_t t[32];
+        tmem_ld32(tDP + lane_off + c * 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float ds[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int qq = c * 32 + g * 8 + e;
+            ds[e] = p[qq] * (__uint_as_float(t[g * 8 + e]) - dl[qq]) * scale;
+          }
+          uint4 v;
+          v.x = pack_bf16x2(ds[0], ds[1]);
+          v.y = pack_bf16x2(ds[2], ds[3]);
+          v.z = pack_bf16x2(ds[4], ds[5]);
+          v.w = pack_bf16x2(ds[6], ds[7]);
+          const int c16 = c * 4 + g;
+          *reinterpret_cast<uint4*>(dsrow + (c16 >> 3) * AB_TILE + (((c16 & 7) ^ (r & 7)) << 4)) = v;
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      if (it > 0) {
+        // dQ of the previous step (overlaps this step's dV/dK MMAs): lane r now means QUERY row r of tile i-1
+        float* dst = dq_acc + (seq0 + (i - 1) * AB_T + r) * d + h * AB_HD;
+#pragma unroll
+        for (int c = 0; c < AB_HD / 32; ++c) {
+          uint32_t t[32];
+          tmem_ld32(tDQ + lane_off + c * 32, t);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4)
+            red_add_f32x4(dst + c * 32 + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
+                          __uint_as_float(t[4 * q4 + 2]), __uint_as_float(t[4 * q4 + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_empty);
+      }
+    }
+
+    // ---- tail: dQ of the last step, then dV / dK of this key tile
+    mbar_wait(dq_full, (n_it - 1) & 1);
+    tc_fence_after();
+    {
+      float* dst = dq_acc + (seq0 + (j + n_it - 1) * AB_T + r) * d + h * AB_HD;
+#pragma unroll
+      for (int c = 0; c < AB_HD / 32; ++c) {
+        uint32_t t[32];
+        tmem_ld32(tDQ + lane_off + c * 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+          red_add_f32x4(dst + c * 32 + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
+                        __uint_as_float(t[4 * q4 + 2]), __uint_as_float(t[4 * q4 + 3]));
+      }
+    }
+    __nv_bfloat16* dk_out = dqkv + (krow0 + r) * (3 * d) + d + h * AB_HD;
+    __nv_bfloat16* dv_out = dqkv + (krow0 + r) * (3 * d) + 2 * d + h * AB_HD;
+#pragma unroll
+    for (int c = 0; c < AB_HD / 32; ++c) {
+      uint32_t t[32];
+      tmem_ld32(tDV + lane_off + c * 32, t);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(t[8 * g + 0]), __uint_as_float(t[8 * g + 1]));
+        v.y = pack_bf16x2(__uint_as_float(t[8 * g + 2]), __uint_as_float(t[8 * g + 3]));
+        v.z = pack_bf16x2(__uint_as_float(t[8 * g + 4]), __uint_as_float(t[8 * g + 5]));
+        v.w = pack_bf16x2(__uint_as_float(t[8 * g + 6]), __uint_as_float(t[8 * g + 7]));
+        *reinterpret_cast<uint4*>(dv_out + c * 32 + g * 8) = v;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < AB_HD / 32; ++c) {
+      uint32_t t[32];
+      tmem_ld32(tDK + lane_off + c * 32, t);
+      tmem_ld_wait();
+      if (rope) {
+        const float4* tab = reinterpret_cast<const float4*>(rope + (static_cast<int64_t>(kj) * (AB_HD >> 1) + c * 16) * 2);
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 cs = __ldg(tab + q4);
+          const float x0 = __uint_as_float(t[4 * q4 + 0]), x1 = __uint_as_float(t[4 * q4 + 1]);
+          const float y0 = __uint_as_float(t[4 * q4 + 2]), y1 = __uint_as_float(t[4 * q4 + 3]);
+          t[4 * q4 + 0] = __float_as_uint(x0 * cs.x + x1 * cs.y);
+          t[4 * q4 + 1] = __float_as_uint(x1 * cs.x - x0 * cs.y);
+          t[4 * q4 + 2] = __float_as_uint(y0 * cs.z + y1 * cs.w);
+          t[4 * q4 + 3] = __float_as_uint(y1 * cs.z - y0 * cs.w);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(t[8 * g + 0]), __uint_as_float(t[8 * g + 1]));
+        v.y = pack_bf16x2(__uint_as_float(t[8 * g + 2]), __uint_as_float(t[8 * g + 3]));
+        v.z = pack_bf16x2(__uint_as_float(t[8 * g + 4]), __uint_as_float(t[8 * g + 5]));
+        v.w = pack_bf16x2(__uint_as_float(t[8 * g + 6]), __uint_as_float(t[8 * g + 7]));
+        *reinterpret_cast<uint4*>(dk_out + c * 32 + g * 8) = v;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace plm
+
+extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                            const int32_t* seg_start, const float* rope_table, void* dqkv, float* delta,
+                            float* dq_acc, int32_t B, int32_t T, int32_t H, int32_t hd, plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_REQUIRE(qkv && out && dout && lse && dqkv && delta && dq_acc, "attn_bwd: null pointer");
+  PLM_REQUIRE(B > 0 && T > 0 && H > 0, "attn_bwd: bad size");
+  if (hd != AB_HD) return fail(PLM_ERR_UNSUPPORTED, "attn_bwd: head_dim %d unsupported (need 64)", hd);
+  if (T % AB_T != 0) return fail(PLM_ERR_UNSUPPORTED, "attn_bwd: seq_len %d must be a multiple of 128", T);
+  PLM_REQUIRE(aligned16(qkv) && aligned16(out) && aligned16(dout) && aligned16(dqkv) && aligned16(dq_acc) &&
+                  (!rope_table || aligned16(rope_table)),
+              "attn_bwd: misaligned pointer");
+  PLM_REQUIRE(static_cast<int64_t>(B) * T < (1ll << 31) && B <= 65535 && H <= 65535, "attn_bwd: size too large");
+
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+  });
+  if (attr_err != cudaSuccess) return fail(PLM_ERR_CUDA, "attn_bwd smem attribute: %s", cudaGetErrorString(attr_err));
+
+  const int d = H * hd;
+  const int64_t rows = static_cast<int64_t>(B) * T;
+  CUtensorMap tmQKV, tmDO;
+  int rc = make_tmap_bf16_2d(&tmQKV, qkv, rows, 3ull * d, 3ull * d, AB_T, 64);
+  if (rc != PLM_OK) return rc;
+  rc = make_tmap_bf16_2d(&tmDO, dout, rows, d, d, AB_T, 64);
+  if (rc != PLM_OK) return rc;
+
+  cudaError_t e = cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * d * sizeof(float), stream);
+  if (e != cudaSuccess) return fail(PLM_ERR_CUDA, "attn_bwd memset: %s", cudaGetErrorString(e));
+
+  {
+    const int64_t n = rows * H * 8;
+    attn_delta_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+        static_cast<const uint4*>(out), static_cast<const uint4*>(dout), delta, rows, T, H);
+    rc = check_launch("attn_delta");
+    if (rc != PLM_OK) return rc;
+  }
+  const float scale = 1.0f / sqrtf(static_cast<float>(hd));
+  dim3 grid(T / AB_T, H, B);
+  attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, lse, delta, seg_start, rope_table,
+                                                         static_cast<__nv_bfloat16*>(dqkv), dq_acc, T, H, scale,
+                                                         scale * 1.4426950408889634f);
+  rc = check_launch("attn_bwd");
+  if (rc != PLM_OK) return rc;
+  {
+    const int64_t n = rows * (d / 8);
+    dq_finalize_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
+        dq_acc, rope_table, static_cast<__nv_bfloat16*>(dqkv), rows, T, d, hd);
+    rc = check_launch("dq_finalize");
+  }
+  return rc;
+}

@@ -1,0 +1,290 @@
+// Causal / document-masked flash-attention forward on tcgen05 (models/transformer.py:53-63).
+//
+// One CTA per (128-query tile, head, batch); 160 threads:
+//   warps 0..3  softmax: thread r owns query row r (TMEM lane r) — row max / sum need no shuffles
+//   warp 4      control: one thread issues the TMA loads (Q once, K/V double-buffered) and all tcgen05.mma
+// Per 128-key tile:  S = Q K^T  (TMEM cols 0..127)  ->  softmax in registers  ->  P (bf16) to swizzled smem
+//                    ->  O += P V  (TMEM cols 128..191, V consumed MN-major straight from its TMA box).
+// O stays in TMEM for the whole row of tiles; it is rescaled only when the running max grows by more than 2^8
+// (lazy rescale), so the common path never round-trips O through registers.  Two CTAs are resident per SM
+// (112 KB smem, 256 TMEM columns each): one CTA's softmax overlaps the other's MMAs.
+// Document masking never touches a dense mask: a row attends keys in [seg_start[row], row]; key tiles entirely
+// before the tile's first document are skipped.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <mutex>
+
+namespace plm {
+
+constexpr int ATT_BQ = 128;   // queries per CTA
+constexpr int ATT_BK = 128;   // keys per tile
+constexpr int ATT_HD = 64;    // head dim
+constexpr int ATT_THREADS = 160;
+constexpr int ATT_TILE_BYTES = ATT_BK * ATT_HD * 2;  // 16 KB
+constexpr int ATT_FWD_SMEM = ATT_TILE_BYTES * (1 + 2 + 2 + 2) + 128;  // Q, K x2, V x2, P (2 blocks) + barriers
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __restrict__ seg_start,
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE_BYTES;
+  uint8_t* sV = smem + 3 * ATT_TILE_BYTES;
+  uint8_t* sP = smem + 5 * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * ATT_TILE_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* pv_done = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+  if ((smem_u32(smem) & 1023u) != 0) return;  // layout contract violated: refuse to run (results stay unwritten)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qt = gridDim.x - 1 - blockIdx.x;  // heavy (late) tiles first
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int d = H * ATT_HD;
+  const int64_t row0 = static_cast<int64_t>(b) * T + qt * ATT_BQ;
+
+  int j_lo = 0;
+  if (seg_start) j_lo = seg_start[row0] / ATT_BK;
+  const int j_hi = qt;
+  const int n_it = j_hi - j_lo + 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    mbar_init(&kv_full[0], 1);
+    mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1);
+    mbar_init(&kv_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc<256>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;
+  const uint32_t tO = tmem_base + 128;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ control thread: TMA + MMA issue
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, ATT_BK, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, ATT_HD, 0, 1);
+      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_2d(sQ, &tmQKV, q_full, h * ATT_HD, static_cast<int>(row0));
+      {
+        const int kr = static_cast<int>(static_cast<int64_t>(b) * T + j_lo * ATT_BK);
+        mbar_arrive_expect_tx(&kv_full[0], 2 * ATT_TILE_BYTES);
+        tma_load_2d(sK, &tmQKV, &kv_full[0], d + h * ATT_HD, kr);
+        tma_load_2d(sV, &tmQKV, &kv_full[0], 2 * d + h * ATT_HD, kr);
+      }
+      mbar_wait(q_full, 0);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1;
+        mbar_wait(&kv_full[st], (it >> 1) & 1);
+        if (it > 0) mbar_wait(s_empty, (it - 1) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ);
+        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+        const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+        const uint32_t p_addr = smem_u32(sP);
+#pragma unroll
+        for (int k = 0; k < ATT_HD / 16; ++k)
+          umma_ss(tS, make_smem_desc_sw128(q_addr + k * 32, 16, 1024), make_smem_desc_sw128(k_addr + k * 32, 16, 1024),
+                  idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+        if (it + 1 < n_it) {  // prefetch next K/V tile
+          const int nst = (it + 1) & 1;
+          mbar_wait(&kv_empty[nst], (((it + 1) >> 1) & 1) ^ 1);
+          const int kr = static_cast<int>(static_cast<int64_t>(b) * T + (j_lo + it + 1) * ATT_BK);
+          mbar_arrive_expect_tx(&kv_full[nst], 2 * ATT_TILE_BYTES);
+          tma_load_2d(sK + nst * ATT_TILE_BYTES, &tmQKV, &kv_full[nst], d + h * ATT_HD, kr);
+          tma_load_2d(sV + nst * ATT_TILE_BYTES, &tmQKV, &kv_full[nst], 2 * d + h * ATT_HD, kr);
+        }
+        mbar_wait(p_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < ATT_BK / 16; ++k)
+          umma_ss(tO, make_smem_desc_sw128(p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
+                  make_smem_desc_sw128(v_addr + k * 2048, ATT_TILE_BYTES, 1024), idesc_o, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warps
+    const int r = warp * 32 + lane;          // row within the tile == TMEM lane
+    const int qi = qt * ATT_BQ + r;          // position within the sequence
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const int seg_lo = seg_start ? seg_start[row0 + r] : 0;
+    float m_run = -INFINITY, l_run = 0.f;
+
+    for (int it = 0; it < n_it; ++it) {
+      const int j = j_lo + it;
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
+      float x[ATT_BK];
+#pragma unroll
+      for (int c = 0; c < ATT_BK / 32; ++c) {
+        uint32_t t[32];
+        tmem_ld32(tS + lane_off + c * 32, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[c * 32 + i] = __uint_as_float(t[i]) * scale_log2;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);
+
+      // mask: key kj = j*128 + c allowed iff seg_lo <= kj <= qi
+      const int kbase = j * ATT_BK;
+      if (kbase + ATT_BK - 1 > qi || kbase < seg_lo) {
+#pragma unroll
+        for (int c = 0; c < ATT_BK; ++c) {
+          const int kj = kbase + c;
+          if (kj > qi || kj < seg_lo) x[c] = -INFINITY;
+        }
+      }
+      float mx = x[0];
+#pragma unroll
+      for (int c = 1; c < ATT_BK; ++c) mx = fmaxf(mx, x[c]);
+
+      // previous P·V must be complete before P smem is overwritten or O is rescaled
+      if (it > 0) {
+        mbar_wait(pv_done, (it - 1) & 1);
+        tc_fence_after();
+      }
+      const bool grow = mx > m_run + 8.0f;
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = fmaxf(m_run, mx);
+        const float alpha = (m_new == -INFINITY) ? 1.0f : ex2(m_run - m_new);  // m_run = -inf -> 0
+        m_run = m_new;
+        l_run *= alpha;
+        if (it > 0) {
+#pragma unroll
+          for (int c = 0; c < ATT_HD / 32; ++c) {
+            uint32_t t[32];
+            tmem_ld32(tO + lane_off + c * 32, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            tmem_st32(tO + lane_off + c * 32, t);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+      float psum = 0.f;
+      uint8_t* prow = sP + r * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < ATT_BK / 8; ++c16) {
+        float p[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          p[i] = ex2(x[c16 * 8 + i] - m_use);
+          psum += p[i];
+        }
+        uint4 v;
+        v.x = pack_bf16x2(p[0], p[1]);
+        v.y = pack_bf16x2(p[2], p[3]);
+        v.z = pack_bf16x2(p[4], p[5]);
+        v.w = pack_bf16x2(p[6], p[7]);
+        const int blk = c16 >> 3, cc = c16 & 7;
+        *reinterpret_cast<uint4*>(prow + blk * ATT_TILE_BYTES + ((cc ^ (r & 7)) << 4)) = v;
+      }
+      l_run += psum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+
+    // ---- epilogue: O / l -> bf16 out[b, t, h, :], lse
+    mbar_wait(pv_done, (n_it - 1) & 1);
+    tc_fence_after();
+    const float inv_l = l_run > 0.f ? 1.0f / l_run : 0.f;
+    __nv_bfloat16* orow = out + (row0 + r) * d + h * ATT_HD;
+#pragma unroll
+    for (int c = 0; c < ATT_HD / 32; ++c) {
+      uint32_t t[32];
+      tmem_ld32(tO + lane_off + c * 32, t);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(t[8 * i + 0]) * inv_l, __uint_as_float(t[8 * i + 1]) * inv_l);
+        v.y = pack_bf16x2(__uint_as_float(t[8 * i + 2]) * inv_l, __uint_as_float(t[8 * i + 3]) * inv_l);
+        v.z = pack_bf16x2(__uint_as_float(t[8 * i + 4]) * inv_l, __uint_as_float(t[8 * i + 5]) * inv_l);
+        v.w = pack_bf16x2(__uint_as_float(t[8 * i + 6]) * inv_l, __uint_as_float(t[8 * i + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(orow + c * 32 + i * 8) = v;
+      }
+    }
+    const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+    lse[(static_cast<int64_t>(b) * H + h) * T + qi] = (m_use + lg2(l_run)) * 0.6931471805599453f;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+}  // namespace plm
+
+extern "C" int plm_attn_fwd(const void* qkv, const int32_t* seg_start, void* out, float* lse, int32_t B, int32_t T,
+                            int32_t H, int32_t hd, plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_REQUIRE(qkv && out && lse, "attn_fwd: null pointer");
+  PLM_REQUIRE(B > 0 && T > 0 && H > 0, "attn_fwd: bad size");
+  if (hd != ATT_HD) return fail(PLM_ERR_UNSUPPORTED, "attn_fwd: head_dim %d unsupported (need 64)", hd);
+  if (T % ATT_BQ != 0) return fail(PLM_ERR_UNSUPPORTED, "attn_fwd: seq_len %d must be a multiple of 128", T);
+  PLM_REQUIRE(aligned16(qkv) && aligned16(out), "attn_fwd: misaligned pointer");
+  PLM_REQUIRE(static_cast<int64_t>(B) * T < (1ll << 31) && B <= 65535 && H <= 65535, "attn_fwd: size too large");
+
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_FWD_SMEM);
+  });
+  if (attr_err != cudaSuccess) return fail(PLM_ERR_CUDA, "attn_fwd smem attribute: %s", cudaGetErrorString(attr_err));
+
+  const int d = H * hd;
+  CUtensorMap tm;
+  int rc = make_tmap_bf16_2d(&tm, qkv, static_cast<uint64_t>(B) * T, 3ull * d, 3ull * d, ATT_BK, 64);
+  if (rc != PLM_OK) return rc;
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(hd));
+  dim3 grid(T / ATT_BQ, H, B);
+  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_FWD_SMEM, stream>>>(tm, seg_start, static_cast<__nv_bfloat16*>(out), lse, T,
+                                                               H, scale_log2);
+  return check_launch("attn_fwd");
+}

@@ -1,0 +1,390 @@
+// tcgen05 GEMM for every nn.Linear of the plainLM train step (models/transformer.py:42,67,114;
+// models/components.py:55-56) — forward, dgrad and wgrad — replacing the cuBLASLt calls PyTorch makes under autocast.
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled boxes, STAGES-deep mbarrier ring)
+//   warp 1      MMA issuer     (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM; owns TMEM alloc/dealloc)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b, one accumulator row per thread, fused epilogues, direct stores)
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of
+// tile i+1.  Tile = 128 x BN x 64 with BN in {128, 256}.  Operands may be K-major or MN-major (UMMA descriptor +
+// instruction-descriptor major bits), which is what lets dgrad and wgrad read activations/weights in place.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <cstdlib>
+#include <mutex>
+
+namespace plm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  void* C;
+  const float* R;
+  const float* rope;
+  int64_t M, N, K;
+  int64_t ldc;
+  int epilogue;
+  int splits;
+  int rope_cols, rope_T, head_dim;
+  int num_m, num_n, kblocks;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+};
+
+__device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_blk, int& n_blk, int& kb0, int& kb1) {
+  const int tiles = p.num_m * p.num_n;
+  const int tile = w % tiles;
+  const int split = w / tiles;
+  m_blk = tile % p.num_m;
+  n_blk = tile / p.num_m;
+  const int per = (p.kblocks + p.splits - 1) / p.splits;
+  kb0 = split * per;
+  kb1 = min(p.kblocks, kb0 + per);
+}
+
+template <int BN, bool A_K, bool B_K>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total = p.num_m * p.num_n * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        int m_blk, n_blk, kb0, kb1;
+        decode_work(p, w, m_blk, n_blk, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          uint8_t* a_dst = sA + s * Cfg::A_BYTES;
+          uint8_t* b_dst = sB + s * Cfg::B_BYTES;
+          if (A_K) {
+            tma_load_2d(a_dst, &tmA, &full[s], kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BM / 64; ++g)
+              tma_load_2d(a_dst + g * (BK * 128), &tmA, &full[s], m_blk * BM + g * 64, kb * BK);
+          }
+          if (B_K) {
+            tma_load_2d(b_dst, &tmB, &full[s], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g)
+              tma_load_2d(b_dst + g * (BK * 128), &tmB, &full[s], n_blk * BN + g * 64, kb * BK);
+          }
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_K ? 0 : 1, B_K ? 0 : 1);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+        int m_blk, n_blk, kb0, kb1;
+        decode_work(p, w, m_blk, n_blk, kb0, kb1);
+        const int a = it & 1;
+        const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(&tempty[a], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + s * Cfg::A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + s * Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = A_K ? make_smem_desc_sw128(a_addr + k * 32, 16, 1024)
+                                       : make_smem_desc_sw128(a_addr + k * 2048, BK * 128, 1024);
+            const uint64_t bdesc = B_K ? make_smem_desc_sw128(b_addr + k * 32, 16, 1024)
+                                       : make_smem_desc_sw128(b_addr + k * 2048, BK * 128, 1024);
+            umma_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
+        }
+        umma_commit(&tfull[a]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    int it = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      int m_blk, n_blk, kb0, kb1;
+      decode_work(p, w, m_blk, n_blk, kb0, kb1);
+      const int a = it & 1;
+      const uint32_t aph = (it >> 1) & 1;
+      mbar_wait(&tfull[a], aph);
+      tc_fence_after();
+      const int64_t row = static_cast<int64_t>(m_blk) * BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int64_t col0 = static_cast<int64_t>(n_blk) * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(t_row + c * 32, r);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        const int ncols = (p.N - col0) < 32 ? static_cast<int>(p.N - col0) : 32;  // multiple of 8
+        if (p.epilogue == PLM_EPI_BF16 || p.epilogue == PLM_EPI_BF16_ROPE) {
+          if (p.epilogue == PLM_EPI_BF16_ROPE && col0 < p.rope_cols) {
+            const int pos = static_cast<int>(row % p.rope_T);
+            const int pair0 = static_cast<int>(col0 % p.head_dim) >> 1;
+            const float4* tab = reinterpret_cast<const float4*>(
+                p.rope + (static_cast<int64_t>(pos) * (p.head_dim >> 1) + pair0) * 2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 cs = __ldg(tab + i);  // (cos0, sin0, cos1, sin1)
+              const float a0 = __uint_as_float(r[4 * i + 0]), b0 = __uint_as_float(r[4 * i + 1]);
+              const float a1 = __uint_as_float(r[4 * i + 2]), b1 = __uint_as_float(r[4 * i + 3]);
+              r[4 * i + 0] = __float_as_uint(a0 * cs.x - b0 * cs.y);
+              r[4 * i + 1] = __float_as_uint(b0 * cs.x + a0 * cs.y);
+              r[4 * i + 2] = __float_as_uint(a1 * cs.z - b1 * cs.w);
+              r[4 * i + 3] = __float_as_uint(b1 * cs.z + a1 * cs.w);
+            }
+          }
+          __nv_bfloat16* cptr = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i * 8 < ncols) {
+              uint4 v;
+              v.x = pack_bf16x2(__uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1]));
+              v.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
+              v.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]));
+              v.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
+              *reinterpret_cast<uint4*>(cptr + i * 8) = v;
+            }
+          }
+        } else {
+          float* cptr = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
+          if (p.epilogue == PLM_EPI_RESID_F32) {
+            const float* rptr = p.R + row * p.ldc + col0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i * 4 < ncols) {
+                const float4 rv = *reinterpret_cast<const float4*>(rptr + i * 4);
+                float4 v;
+                v.x = rv.x + __uint_as_float(r[4 * i + 0]);
+                v.y = rv.y + __uint_as_float(r[4 * i + 1]);
+                v.z = rv.z + __uint_as_float(r[4 * i + 2]);
+                v.w = rv.w + __uint_as_float(r[4 * i + 3]);
+                *reinterpret_cast<float4*>(cptr + i * 4) = v;
+              }
+            }
+          } else if (p.epilogue == PLM_EPI_ATOMIC_F32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i * 4 < ncols)
+                red_add_f32x4(cptr + i * 4, __uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1]),
+                              __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i * 4 < ncols) {
+                float4 v;
+                v.x = __uint_as_float(r[4 * i + 0]);
+                v.y = __uint_as_float(r[4 * i + 1]);
+                v.z = __uint_as_float(r[4 * i + 2]);
+                v.w = __uint_as_float(r[4 * i + 3]);
+                *reinterpret_cast<float4*>(cptr + i * 4) = v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[a]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, bool A_K, bool B_K>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_kernel<BN, A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return fail(PLM_ERR_CUDA, "gemm smem attribute: %s", cudaGetErrorString(attr_err));
+  const int total = p.num_m * p.num_n * p.splits;
+  const int grid = total < sm_count() ? total : sm_count();
+  gemm_kernel<BN, A_K, B_K><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  return check_launch("gemm_kernel");
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+}  // namespace plm
+
+extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_REQUIRE(a != nullptr, "gemm: null args");
+  PLM_REQUIRE(a->A && a->B && a->C, "gemm: null operand");
+  PLM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "gemm: non-positive size M=%lld N=%lld K=%lld", (long long)a->M,
+              (long long)a->N, (long long)a->K);
+  PLM_REQUIRE(a->M < (1ll << 31) && a->N < (1ll << 31) && a->K < (1ll << 31), "gemm: size too large");
+  PLM_REQUIRE(aligned16(a->A) && aligned16(a->B) && aligned16(a->C), "gemm: operands must be 16-byte aligned");
+  PLM_REQUIRE(a->N % 8 == 0 && a->lda % 8 == 0 && a->ldb % 8 == 0 && a->ldc % 8 == 0,
+              "gemm: N and leading dimensions must be multiples of 8");
+  PLM_REQUIRE(a->epilogue >= PLM_EPI_BF16 && a->epilogue <= PLM_EPI_ATOMIC_F32, "gemm: bad epilogue %d", a->epilogue);
+  if (a->epilogue == PLM_EPI_RESID_F32) PLM_REQUIRE(a->R && aligned16(a->R), "gemm: residual pointer missing/misaligned");
+  if (a->epilogue == PLM_EPI_BF16_ROPE) {
+    PLM_REQUIRE(a->rope_table && aligned16(a->rope_table), "gemm: rope table missing/misaligned");
+    PLM_REQUIRE(a->head_dim >= 32 && a->head_dim % 32 == 0 && a->rope_T > 0 && a->rope_cols % a->head_dim == 0,
+                "gemm: bad rope geometry");
+  }
+  const bool a_k = a->a_kmajor != 0, b_k = a->b_kmajor != 0;
+  PLM_REQUIRE(a->lda >= (a_k ? a->K : a->M) && a->ldb >= (b_k ? a->K : a->N) && a->ldc >= a->N,
+              "gemm: leading dimension too small");
+
+  GemmParams p;
+  p.C = a->C;
+  p.R = a->R;
+  p.rope = a->rope_table;
+  p.M = a->M;
+  p.N = a->N;
+  p.K = a->K;
+  p.ldc = a->ldc;
+  p.epilogue = a->epilogue;
+  p.rope_cols = a->rope_cols;
+  p.rope_T = a->rope_T;
+  p.head_dim = a->head_dim;
+  p.kblocks = static_cast<int>((a->K + BK - 1) / BK);
+  p.num_m = static_cast<int>((a->M + BM - 1) / BM);
+
+  // Tile width: fewer, wider tiles feed the tensor core best (one 128x256x16 MMA reads 12 KB of smem per 128 cycles);
+  // fall back to BN=128 when 256-wide tiles leave a badly quantised last wave.
+  const int sms = sm_count();
+  int bn = 256;
+  {
+    const int64_t t256 = p.num_m * ((a->N + 255) / 256), t128 = p.num_m * ((a->N + 127) / 128);
+    const double c256 = static_cast<double>((t256 + sms - 1) / sms) * 1.0;
+    const double c128 = static_cast<double>((t128 + sms - 1) / sms) * 0.55;
+    if (a->N <= 128 || c128 < c256) bn = 128;
+    const int forced = env_int("PLM_GEMM_BN", 0);
+    if (forced == 128 || forced == 256) bn = forced;
+  }
+  p.num_n = static_cast<int>((a->N + bn - 1) / bn);
+
+  int splits = a->splits;
+  if (a->epilogue != PLM_EPI_ATOMIC_F32) {
+    PLM_REQUIRE(splits <= 1, "gemm: split-K needs the atomic epilogue");
+    splits = 1;
+  } else if (splits <= 0) {
+    const int tiles = p.num_m * p.num_n;
+    splits = 1;
+    if (tiles < sms) splits = (sms + tiles - 1) / tiles;
+    const int max_splits = p.kblocks / 8 > 0 ? p.kblocks / 8 : 1;  // keep >= 8 k-blocks per split
+    if (splits > max_splits) splits = max_splits;
+  }
+  if (splits > p.kblocks) splits = p.kblocks;
+  {
+    const int per = (p.kblocks + splits - 1) / splits;
+    splits = (p.kblocks + per - 1) / per;  // no empty split
+  }
+  p.splits = splits;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (a_k)
+    rc = make_tmap_bf16_2d(&tmA, a->A, a->M, a->K, a->lda, BM, 64);
+  else
+    rc = make_tmap_bf16_2d(&tmA, a->A, a->K, a->M, a->lda, BK, 64);
+  if (rc != PLM_OK) return rc;
+  if (b_k)
+    rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, bn, 64);
+  else
+    rc = make_tmap_bf16_2d(&tmB, a->B, a->K, a->N, a->ldb, BK, 64);
+  if (rc != PLM_OK) return rc;
+
+#define PLM_DISPATCH(BN_)                                                        \
+  if (a_k && b_k) return launch_gemm<BN_, true, true>(tmA, tmB, p, stream);      \
+  if (a_k && !b_k) return launch_gemm<BN_, true, false>(tmA, tmB, p, stream);    \
+  if (!a_k && b_k) return launch_gemm<BN_, false, true>(tmA, tmB, p, stream);    \
+  return launch_gemm<BN_, false, false>(tmA, tmB, p, stream);
+  if (bn == 256) {
+    PLM_DISPATCH(256)
+  } else {
+    PLM_DISPATCH(128)
+  }
+#undef PLM_DISPATCH
+}

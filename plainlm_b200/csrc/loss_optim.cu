@@ -1,0 +1,364 @@
+// Cross-entropy (engine/engine.py:81,110-112), gradient-norm (engine/engine.py:126-128) and the parameter updates
+// (optim/init_optim.py:13-21 -> torch fused AdamW; optim/signSGD.py:21-46) as flat-buffer bandwidth kernels.
+#include "common.cuh"
+#include "ptx.cuh"
+
+#include <math.h>
+
+namespace plm {
+
+// ------------------------------------------------------------------------------------------- cross-entropy
+struct MS {
+  float m, s;
+};
+__device__ __forceinline__ MS ms_combine(MS a, MS b) {
+  MS r;
+  r.m = fmaxf(a.m, b.m);
+  if (r.m == -INFINITY) {
+    r.s = 0.f;
+    return r;
+  }
+  r.s = a.s * __expf(a.m - r.m) + b.s * __expf(b.m - r.m);
+  return r;
+}
+
+__device__ __forceinline__ bool ce_ignored(int64_t t, int V) { return t < 0 || t >= V; }
+
+// One block per row: online max / sum-exp over V bf16 logits; row_lse = logsumexp, row_loss = lse - logit[target].
+__global__ void __launch_bounds__(256)
+ce_stats_kernel(const __nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ targets,
+                float* __restrict__ row_loss, float* __restrict__ row_lse, int V, int64_t ldl) {
+  __shared__ MS red[8];
+  const int64_t row = blockIdx.x;
+  const uint4* lp = reinterpret_cast<const uint4*>(logits + row * ldl);
+  MS acc = {-INFINITY, 0.f};
+  const int V8 = V >> 3;
+  for (int i = threadIdx.x; i < V8; i += blockDim.x) {
+    const uint4 v = __ldg(lp + i);
+    float x[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                  bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+    float mx = x[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) mx = fmaxf(mx, x[k]);
+    const float nm = fmaxf(acc.m, mx);
+    float s = acc.s * __expf(acc.m - nm);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += __expf(x[k] - nm);
+    acc.m = nm;
+    acc.s = s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MS other;
+    other.m = __shfl_xor_sync(0xffffffffu, acc.m, o);
+    other.s = __shfl_xor_sync(0xffffffffu, acc.s, o);
+    acc = ms_combine(acc, other);
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    MS t = red[0];
+    for (int k = 1; k < 8; ++k) t = ms_combine(t, red[k]);
+    const float lse = t.m + logf(t.s);
+    row_lse[row] = lse;
+    const int64_t tgt = targets[row];
+    row_loss[row] = ce_ignored(tgt, V) ? 0.f : lse - __bfloat162float(logits[row * ldl + tgt]);
+  }
+}
+
+// Single block: stats[0] = sum of row losses, stats[1] = #valid rows, stats[2] = mean. Fixed order.
+__global__ void __launch_bounds__(1024)
+ce_reduce_kernel(const float* __restrict__ row_loss, const int64_t* __restrict__ targets, float* __restrict__ stats,
+                 int64_t rows, int V) {
+  __shared__ float ssum[32];
+  __shared__ float scnt[32];
+  float s = 0.f, c = 0.f;
+  for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) {
+    s += row_loss[i];
+    c += ce_ignored(targets[i], V) ? 0.f : 1.f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    ssum[threadIdx.x >> 5] = s;
+    scnt[threadIdx.x >> 5] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ts = 0.f, tc = 0.f;
+    for (int k = 0; k < 32; ++k) {
+      ts += ssum[k];
+      tc += scnt[k];
+    }
+    stats[0] = ts;
+    stats[1] = tc;
+    stats[2] = tc > 0.f ? ts / tc : nanf("");  // torch returns nan when every target is ignored
+  }
+}
+
+// dlogits = (softmax - onehot) * grad_scale / n_valid, written over the logits (bf16).
+__global__ void __launch_bounds__(256)
+ce_grad_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ targets,
+               const float* __restrict__ row_lse, const float* __restrict__ stats, int V, int64_t ldl,
+               float grad_scale) {
+  const int64_t row = blockIdx.x;
+  uint4* lp = reinterpret_cast<uint4*>(logits + row * ldl);
+  const int64_t tgt = targets[row];
+  const int V8 = V >> 3;
+  if (ce_ignored(tgt, V)) {
+    for (int i = threadIdx.x; i < V8; i += blockDim.x) lp[i] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const float lse = row_lse[row];
+  const float scale = grad_scale / stats[1];
+  const int t8 = static_cast<int>(tgt >> 3), tk = static_cast<int>(tgt & 7);
+  for (int i = threadIdx.x; i < V8; i += blockDim.x) {
+    const uint4 v = lp[i];
+    float x[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                  bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float p = __expf(x[k] - lse);
+      if (i == t8 && k == tk) p -= 1.0f;
+      x[k] = p * scale;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(x[0], x[1]);
+    o.y = pack_bf16x2(x[2], x[3]);
+    o.z = pack_bf16x2(x[4], x[5]);
+    o.w = pack_bf16x2(x[6], x[7]);
+    lp[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- sum of squares
+constexpr int SUMSQ_BLOCKS = 592;  // 4 per SM; must be <= PLM_SUMSQ_WORKSPACE
+
+__global__ void __launch_bounds__(256)
+sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ partial) {
+  __shared__ float red[8];
+  const int64_t n4 = n >> 2;
+  // contiguous chunk per block, fixed thread->element mapping => deterministic
+  const int64_t per = (n4 + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = per * blockIdx.x, hi = min(n4, lo + per);
+  float s = 0.f;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float v = g[(n4 << 2) + threadIdx.x];
+    s += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+sumsq_final_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ out, int accumulate) {
+  float s = 0.f;
+  for (int i = threadIdx.x; i < nblocks; i += 32) s += partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) out[0] = accumulate ? out[0] + s : s;
+}
+
+// ------------------------------------------------------------------------------------------- optimizers
+__device__ __forceinline__ float clip_coef(const float* gnorm_sq, float max_norm) {
+  if (gnorm_sq == nullptr || max_norm <= 0.f) return 1.0f;
+  const float norm = sqrtf(*gnorm_sq);
+  const float c = max_norm / (norm + 1e-6f);  // torch.nn.utils.clip_grad_norm_: clamp(max_norm / (norm + 1e-6), max=1)
+  return c < 1.0f ? c : 1.0f;
+}
+
+struct AdamArgs {
+  float lr, one_minus_b1, b2, one_minus_b2, eps, lr_wd, step_size, bc2_sqrt, max_norm;
+};
+
+__device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v, const AdamArgs& a) {
+  p -= a.lr_wd * p;
+  m = m + a.one_minus_b1 * (g - m);
+  v = a.b2 * v + a.one_minus_b2 * g * g;
+  const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+  p -= a.step_size * m / denom;
+}
+
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+             __nv_bfloat16* __restrict__ pb, int64_t n, AdamArgs a, const float* __restrict__ gnorm_sq) {
+  const float clip = clip_coef(gnorm_sq, a.max_norm);
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adamw_elem(pv.x, gv.x * clip, mv.x, vv.x, a);
+    adamw_elem(pv.y, gv.y * clip, mv.y, vv.y, a);
+    adamw_elem(pv.z, gv.z * clip, mv.z, vv.z, a);
+    adamw_elem(pv.w, gv.w * clip, mv.w, vv.w, a);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (pb) {
+      uint2 o;
+      o.x = pack_bf16x2(pv.x, pv.y);
+      o.y = pack_bf16x2(pv.z, pv.w);
+      reinterpret_cast<uint2*>(pb)[i] = o;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    float pv = p[i], mv = m[i], vv = v[i];
+    adamw_elem(pv, g[i] * clip, mv, vv, a);
+    p[i] = pv;
+    m[i] = mv;
+    v[i] = vv;
+    if (pb) pb[i] = __float2bfloat16_rn(pv);
+  }
+}
+
+__device__ __forceinline__ float signf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+
+__device__ __forceinline__ void signsgd_elem(float& p, float g, float& m, float lr, float mu, float omd, float decay,
+                                             int first) {
+  p *= decay;
+  const float m0 = first ? g : m;  // optim/signSGD.py:38-39: m initialised to a clone of the gradient
+  m = m0 * mu + omd * g;
+  p -= lr * signf(m);
+}
+
+__global__ void __launch_bounds__(256)
+signsgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+               __nv_bfloat16* __restrict__ pb, int64_t n, float lr, float mu, float omd, float decay, int first,
+               const float* __restrict__ gnorm_sq, float max_norm) {
+  const float clip = clip_coef(gnorm_sq, max_norm);
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(m)[i];
+    signsgd_elem(pv.x, gv.x * clip, mv.x, lr, mu, omd, decay, first);
+    signsgd_elem(pv.y, gv.y * clip, mv.y, lr, mu, omd, decay, first);
+    signsgd_elem(pv.z, gv.z * clip, mv.z, lr, mu, omd, decay, first);
+    signsgd_elem(pv.w, gv.w * clip, mv.w, lr, mu, omd, decay, first);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    if (pb) {
+      uint2 o;
+      o.x = pack_bf16x2(pv.x, pv.y);
+      o.y = pack_bf16x2(pv.z, pv.w);
+      reinterpret_cast<uint2*>(pb)[i] = o;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    float pv = p[i], mv = first ? 0.f : m[i];
+    signsgd_elem(pv, g[i] * clip, mv, lr, mu, omd, decay, first);
+    p[i] = pv;
+    m[i] = mv;
+    if (pb) pb[i] = __float2bfloat16_rn(pv);
+  }
+}
+
+static unsigned flat_grid(int64_t n4) {
+  int64_t blocks = (n4 + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<unsigned>(blocks);
+}
+
+}  // namespace plm
+
+extern "C" {
+
+int plm_ce_fwd_bwd(void* logits, const int64_t* targets, float* row_loss, float* row_lse, float* stats, int64_t rows,
+                   int32_t V, int64_t ldl, float grad_scale, int32_t write_grad, plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_REQUIRE(logits && targets && row_loss && row_lse && stats, "ce: null pointer");
+  PLM_REQUIRE(rows > 0 && V > 0 && ldl >= V, "ce: bad size");
+  PLM_REQUIRE(V % 8 == 0 && ldl % 8 == 0 && aligned16(logits), "ce: V, ldl must be multiples of 8, logits aligned");
+  PLM_REQUIRE(rows < (1ll << 31), "ce: too many rows");
+  __nv_bfloat16* lg = static_cast<__nv_bfloat16*>(logits);
+  ce_stats_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(lg, targets, row_loss, row_lse, V, ldl);
+  int rc = check_launch("ce_stats");
+  if (rc != PLM_OK) return rc;
+  ce_reduce_kernel<<<1, 1024, 0, stream>>>(row_loss, targets, stats, rows, V);
+  rc = check_launch("ce_reduce");
+  if (rc != PLM_OK) return rc;
+  if (write_grad) {
+    ce_grad_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(lg, targets, row_lse, stats, V, ldl, grad_scale);
+    rc = check_launch("ce_grad");
+  }
+  return rc;
+}
+
+int plm_sumsq(const float* g, int64_t n, float* workspace, float* out, int32_t accumulate, plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  static_assert(SUMSQ_BLOCKS <= PLM_SUMSQ_WORKSPACE, "workspace too small");
+  PLM_REQUIRE(g && workspace && out && n >= 0, "sumsq: bad argument");
+  PLM_REQUIRE(aligned16(g), "sumsq: misaligned pointer");
+  sumsq_partial_kernel<<<SUMSQ_BLOCKS, 256, 0, stream>>>(g, n, workspace);
+  int rc = check_launch("sumsq_partial");
+  if (rc != PLM_OK) return rc;
+  sumsq_final_kernel<<<1, 32, 0, stream>>>(workspace, SUMSQ_BLOCKS, out, accumulate);
+  return check_launch("sumsq_final");
+}
+
+int plm_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, float bc1, float bc2, const float* gnorm_sq,
+                   float max_norm, plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_REQUIRE(p && g && m && v && n >= 0, "adamw: bad argument");
+  PLM_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "adamw: misaligned pointer");
+  PLM_REQUIRE(!p_bf16 || (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0, "adamw: misaligned bf16 shadow");
+  PLM_REQUIRE(bc1 > 0.f && bc2 > 0.f, "adamw: bias corrections must be positive (step >= 1)");
+  if (n == 0) return PLM_OK;
+  AdamArgs a;
+  a.lr = lr;
+  a.one_minus_b1 = static_cast<float>(1.0 - static_cast<double>(beta1));
+  a.b2 = beta2;
+  a.one_minus_b2 = static_cast<float>(1.0 - static_cast<double>(beta2));
+  a.eps = eps;
+  a.lr_wd = lr * weight_decay;
+  a.step_size = lr / bc1;
+  a.bc2_sqrt = sqrtf(bc2);
+  a.max_norm = max_norm;
+  adamw_kernel<<<flat_grid(n >> 2), 256, 0, stream>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p_bf16), n, a, gnorm_sq);
+  return check_launch("adamw");
+}
+
+int plm_signsgd_step(float* p, const float* g, float* m, void* p_bf16, int64_t n, float lr, float momentum,
+                     float dampening, float weight_decay, int32_t first_step, const float* gnorm_sq, float max_norm,
+                     plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_REQUIRE(p && g && m && n >= 0, "signsgd: bad argument");
+  PLM_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m), "signsgd: misaligned pointer");
+  PLM_REQUIRE(!p_bf16 || (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0, "signsgd: misaligned bf16 shadow");
+  if (n == 0) return PLM_OK;
+  signsgd_kernel<<<flat_grid(n >> 2), 256, 0, stream>>>(p, g, m, static_cast<__nv_bfloat16*>(p_bf16), n, lr, momentum,
+                                                         static_cast<float>(1.0 - static_cast<double>(dampening)),
+                                                         static_cast<float>(1.0 - static_cast<double>(lr) * weight_decay),
+                                                         first_step ? 1 : 0,
+                                                         gnorm_sq, max_norm);
+  return check_launch("signsgd");
+}
+
+}  // extern "C"

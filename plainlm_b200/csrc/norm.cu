@@ -1,0 +1,211 @@
+// RMSNorm forward / backward (models/components.py:16-28) as single-pass bandwidth kernels.
+// One warp owns one row; the row lives in registers (d = 128 * VPL, float4 per lane per 128 columns), reductions are
+// warp shuffles, every global access is a 128-bit vector.  Forward: 4 B/elt read + 2 B/elt write.
+// Backward: reads dy (2) + x (4) [+ dx_in (4)], writes dx (4) [+ bf16 copy (2)]; dw partial sums stay in registers
+// across the rows a warp visits and are reduced once per block.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace plm {
+
+constexpr int NORM_WARPS = 8;
+constexpr int NORM_BWD_MAX_BLOCKS = 296;  // 2 per SM
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __nv_bfloat16* __restrict__ y,
+                   float* __restrict__ rstd, int64_t rows, float eps) {
+  constexpr int D = VPL * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * NORM_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  float4 v[VPL];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = __ldcs(xr + i * 32 + lane);
+    ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  }
+  ss = warp_sum(ss);
+  const float r = rsqrtf(ss / D + eps);
+  if (lane == 0) rstd[row] = r;
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  uint2* yr = reinterpret_cast<uint2*>(y + row * D);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float4 ww = __ldg(wr + i * 32 + lane);
+    uint2 o;
+    o.x = pack_bf16x2(v[i].x * r * ww.x, v[i].y * r * ww.y);
+    o.y = pack_bf16x2(v[i].z * r * ww.z, v[i].w * r * ww.w);
+    yr[i * 32 + lane] = o;
+  }
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+                   const float* __restrict__ rstd, const float* dx_in, float* dx_out,
+                   __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dw_partial, int64_t rows) {
+  constexpr int D = VPL * 128;
+  __shared__ float4 red[NORM_WARPS][32];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  float4 ww[VPL], dw[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    ww[i] = __ldg(wr + i * 32 + lane);
+    dw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * NORM_WARPS + warp; row < rows;
+       row += static_cast<int64_t>(gridDim.x) * NORM_WARPS) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    const uint2* dyr = reinterpret_cast<const uint2*>(dy + row * D);
+    const float r = rstd[row];
+    float4 xh[VPL], g[VPL];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float4 xv = __ldcs(xr + i * 32 + lane);
+      const uint2 dv = __ldcs(dyr + i * 32 + lane);
+      const float d0 = bf16_lo(dv.x), d1 = bf16_hi(dv.x), d2 = bf16_lo(dv.y), d3 = bf16_hi(dv.y);
+      xh[i] = make_float4(xv.x * r, xv.y * r, xv.z * r, xv.w * r);
+      g[i] = make_float4(d0 * ww[i].x, d1 * ww[i].y, d2 * ww[i].z, d3 * ww[i].w);
+      dot += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+      dw[i].x += d0 * xh[i].x;
+      dw[i].y += d1 * xh[i].y;
+      dw[i].z += d2 * xh[i].z;
+      dw[i].w += d3 * xh[i].w;
+    }
+    dot = warp_sum(dot) * (1.0f / D);
+    float4* dxo = reinterpret_cast<float4*>(dx_out + row * D);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      float4 o;
+      o.x = r * (g[i].x - xh[i].x * dot);
+      o.y = r * (g[i].y - xh[i].y * dot);
+      o.z = r * (g[i].z - xh[i].z * dot);
+      o.w = r * (g[i].w - xh[i].w * dot);
+      if (dx_in) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(dx_in + row * D) + i * 32 + lane);
+        o.x += a.x;
+        o.y += a.y;
+        o.z += a.z;
+        o.w += a.w;
+      }
+      dxo[i * 32 + lane] = o;
+      if (dx_bf16) {
+        uint2 b;
+        b.x = pack_bf16x2(o.x, o.y);
+        b.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(dx_bf16 + row * D)[i * 32 + lane] = b;
+      }
+    }
+  }
+  // block reduction of the dw partials, fixed order (warp 0..7) => deterministic
+  float4* out = reinterpret_cast<float4*>(dw_partial + static_cast<int64_t>(blockIdx.x) * D);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    red[warp][lane] = dw[i];
+    __syncthreads();
+    if (warp == 0) {
+      float4 s = red[0][lane];
+#pragma unroll
+      for (int k = 1; k < NORM_WARPS; ++k) {
+        const float4 t = red[k][lane];
+        s.x += t.x;
+        s.y += t.y;
+        s.z += t.z;
+        s.w += t.w;
+      }
+      out[i * 32 + lane] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// dw[c] += sum_b partial[b, c], fixed order.
+__global__ void colsum_accum_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nblocks, int d) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[static_cast<int64_t>(b) * d + c];
+  dw[c] += s;
+}
+
+static int norm_bwd_blocks(int64_t rows) {
+  int64_t b = (rows + NORM_WARPS - 1) / NORM_WARPS;
+  if (b > NORM_BWD_MAX_BLOCKS) b = NORM_BWD_MAX_BLOCKS;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace plm
+
+#define PLM_VPL_SWITCH(vpl, CALL)                                          \
+  switch (vpl) {                                                           \
+    case 1: { constexpr int V = 1; CALL; } break;                          \
+    case 2: { constexpr int V = 2; CALL; } break;                          \
+    case 3: { constexpr int V = 3; CALL; } break;                          \
+    case 4: { constexpr int V = 4; CALL; } break;                          \
+    case 6: { constexpr int V = 6; CALL; } break;                          \
+    case 8: { constexpr int V = 8; CALL; } break;                          \
+    case 12: { constexpr int V = 12; CALL; } break;                        \
+    case 16: { constexpr int V = 16; CALL; } break;                        \
+    default:                                                               \
+      return plm::fail(PLM_ERR_UNSUPPORTED, "rmsnorm: d=%d not in {128,256,384,512,768,1024,1536,2048}", d); \
+  }
+
+extern "C" {
+
+int plm_rmsnorm_fwd(const float* x, const float* w, void* y_bf16, float* rstd, int64_t rows, int32_t d, float eps,
+                    plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_REQUIRE(x && w && y_bf16 && rstd, "rmsnorm_fwd: null pointer");
+  PLM_REQUIRE(rows >= 0 && d > 0, "rmsnorm_fwd: bad size");
+  PLM_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y_bf16), "rmsnorm_fwd: misaligned pointer");
+  if (d % 128 != 0) return fail(PLM_ERR_UNSUPPORTED, "rmsnorm: d=%d must be a multiple of 128", d);
+  if (rows == 0) return PLM_OK;
+  const int blocks = static_cast<int>((rows + NORM_WARPS - 1) / NORM_WARPS);
+  PLM_VPL_SWITCH(d / 128, (rmsnorm_fwd_kernel<V><<<blocks, NORM_WARPS * 32, 0, stream>>>(
+                              x, w, static_cast<__nv_bfloat16*>(y_bf16), rstd, rows, eps)));
+  return check_launch("rmsnorm_fwd");
+}
+
+int plm_rmsnorm_bwd_blocks(int64_t rows) { return plm::norm_bwd_blocks(rows); }
+
+int plm_rmsnorm_bwd(const void* dy_bf16, const float* x, const float* w, const float* rstd, const float* dx_in,
+                    float* dx_out, void* dx_out_bf16, float* dw_partial, int64_t rows, int32_t d,
+                    plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_REQUIRE(dy_bf16 && x && w && rstd && dx_out && dw_partial, "rmsnorm_bwd: null pointer");
+  PLM_REQUIRE(rows > 0 && d > 0, "rmsnorm_bwd: bad size");
+  PLM_REQUIRE(aligned16(dy_bf16) && aligned16(x) && aligned16(w) && aligned16(dx_out) && aligned16(dw_partial) &&
+                  (!dx_in || aligned16(dx_in)) && (!dx_out_bf16 || aligned16(dx_out_bf16)),
+              "rmsnorm_bwd: misaligned pointer");
+  if (d % 128 != 0) return fail(PLM_ERR_UNSUPPORTED, "rmsnorm: d=%d must be a multiple of 128", d);
+  const int blocks = norm_bwd_blocks(rows);
+  PLM_VPL_SWITCH(d / 128, (rmsnorm_bwd_kernel<V><<<blocks, NORM_WARPS * 32, 0, stream>>>(
+                              static_cast<const __nv_bfloat16*>(dy_bf16), x, w, rstd, dx_in, dx_out,
+                              static_cast<__nv_bfloat16*>(dx_out_bf16), dw_partial, rows)));
+  return check_launch("rmsnorm_bwd");
+}
+
+int plm_colsum_accum(const float* partial, float* dw, int32_t nblocks, int32_t d, plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_REQUIRE(partial && dw && nblocks > 0 && d > 0, "colsum_accum: bad argument");
+  colsum_accum_kernel<<<(d + 127) / 128, 128, 0, stream>>>(partial, dw, nblocks, d);
+  return check_launch("colsum_accum");
+}
+
+}  // extern "C"

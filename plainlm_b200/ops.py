@@ -1,0 +1,215 @@
+"""Tensor-level wrappers over the C ABI: torch tensors in, device pointers + current CUDA stream out.
+
+PyTorch is used only for device memory and streams; every function here ends in exactly one `plm_*` call.
+All functions require CUDA tensors and raise otherwise (no CPU path).
+"""
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, check
+
+
+def _stream():
+  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, dtype=None, name='tensor'):
+  if t is None:
+    return None
+  if not t.is_cuda:
+    raise RuntimeError(f'plainlm_b200: {name} must be a CUDA tensor (no CPU path)')
+  if dtype is not None and t.dtype != dtype:
+    raise TypeError(f'plainlm_b200: {name} must be {dtype}, got {t.dtype}')
+  return ctypes.c_void_p(t.data_ptr())
+
+
+def _rowmajor_ld(t, name):
+  if t.dim() != 2 or t.stride(1) != 1:
+    raise ValueError(f'plainlm_b200: {name} must be 2-D with unit inner stride, got strides {t.stride()}')
+  return t.stride(0)
+
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_BF16, residual=None, rope_table=None,
+         rope_cols=0, rope_T=0, head_dim=0, splits=1):
+  """out[M,N] = contraction of a and b (see include/plainlm_b200.h, plm_gemm_bf16).
+
+  a: [M,K] if a_kmajor else [K,M];  b: [N,K] if b_kmajor else [K,N];  bf16, unit inner stride.
+  """
+  lib = _lib.load()
+  lda, ldb, ldc = _rowmajor_ld(a, 'a'), _rowmajor_ld(b, 'b'), _rowmajor_ld(out, 'out')
+  M, K = (a.shape[0], a.shape[1]) if a_kmajor else (a.shape[1], a.shape[0])
+  N, Kb = (b.shape[0], b.shape[1]) if b_kmajor else (b.shape[1], b.shape[0])
+  if K != Kb or out.shape[0] != M or out.shape[1] != N:
+    raise ValueError(f'plainlm_b200.gemm: shape mismatch a={tuple(a.shape)} b={tuple(b.shape)} out={tuple(out.shape)}')
+  out_dtype = bf16 if epilogue in (_lib.EPI_BF16, _lib.EPI_BF16_ROPE) else f32
+  args = GemmArgs()
+  args.A, args.B, args.C = _ptr(a, bf16, 'a'), _ptr(b, bf16, 'b'), _ptr(out, out_dtype, 'out')
+  if residual is not None:
+    if residual.shape != out.shape or _rowmajor_ld(residual, 'residual') != ldc:
+      raise ValueError('plainlm_b200.gemm: residual must match out in shape and leading dimension')
+  args.R = _ptr(residual, f32, 'residual')
+  args.rope_table = _ptr(rope_table, f32, 'rope_table')
+  args.M, args.N, args.K = M, N, K
+  args.lda, args.ldb, args.ldc = lda, ldb, ldc
+  args.a_kmajor, args.b_kmajor = int(a_kmajor), int(b_kmajor)
+  args.epilogue, args.splits = epilogue, splits
+  args.rope_cols, args.rope_T, args.head_dim = rope_cols, rope_T, head_dim
+  check(lib.plm_gemm_bf16(ctypes.byref(args), _stream()), 'plm_gemm_bf16')
+  return out
+
+
+# ---------------------------------------------------------------------------------------------- attention
+def attn_fwd(qkv, out, lse, B, T, H, hd, seg_start=None):
+  lib = _lib.load()
+  check(lib.plm_attn_fwd(_ptr(qkv, bf16, 'qkv'), _ptr(seg_start, torch.int32, 'seg_start'), _ptr(out, bf16, 'out'),
+                         _ptr(lse, f32, 'lse'), B, T, H, hd, _stream()), 'plm_attn_fwd')
+  return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd, seg_start=None, rope_table=None):
+  lib = _lib.load()
+  check(lib.plm_attn_bwd(_ptr(qkv, bf16, 'qkv'), _ptr(out, bf16, 'out'), _ptr(dout, bf16, 'dout'),
+                         _ptr(lse, f32, 'lse'), _ptr(seg_start, torch.int32, 'seg_start'),
+                         _ptr(rope_table, f32, 'rope_table'), _ptr(dqkv, bf16, 'dqkv'), _ptr(delta, f32, 'delta'),
+                         _ptr(dq_acc, f32, 'dq_acc'), B, T, H, hd, _stream()), 'plm_attn_bwd')
+  return dqkv
+
+
+def rope_qk_(qkv, rope_table, T, H, hd, inverse=False):
+  lib = _lib.load()
+  rows = qkv.numel() // (3 * H * hd)
+  check(lib.plm_rope_qk(_ptr(qkv, bf16, 'qkv'), _ptr(rope_table, f32, 'rope_table'), rows, T, H, hd,
+                        -1 if inverse else 1, _stream()), 'plm_rope_qk')
+  return qkv
+
+
+# ---------------------------------------------------------------------------------------------- RMSNorm
+def rmsnorm_fwd(x, w, y, rstd, eps):
+  lib = _lib.load()
+  d = x.shape[-1]
+  rows = x.numel() // d
+  check(lib.plm_rmsnorm_fwd(_ptr(x, f32, 'x'), _ptr(w, f32, 'w'), _ptr(y, bf16, 'y'), _ptr(rstd, f32, 'rstd'), rows, d,
+                            float(eps), _stream()), 'plm_rmsnorm_fwd')
+  return y, rstd
+
+
+def rmsnorm_bwd_blocks(rows):
+  return _lib.load().plm_rmsnorm_bwd_blocks(rows)
+
+
+def rmsnorm_bwd(dy, x, w, rstd, dx_in, dx_out, dx_out_bf16, dw_partial):
+  lib = _lib.load()
+  d = x.shape[-1]
+  rows = x.numel() // d
+  check(lib.plm_rmsnorm_bwd(_ptr(dy, bf16, 'dy'), _ptr(x, f32, 'x'), _ptr(w, f32, 'w'), _ptr(rstd, f32, 'rstd'),
+                            _ptr(dx_in, f32, 'dx_in'), _ptr(dx_out, f32, 'dx_out'),
+                            _ptr(dx_out_bf16, bf16, 'dx_out_bf16'), _ptr(dw_partial, f32, 'dw_partial'), rows, d,
+                            _stream()), 'plm_rmsnorm_bwd')
+  return dx_out
+
+
+def colsum_accum(partial, dw, nblocks):
+  lib = _lib.load()
+  check(lib.plm_colsum_accum(_ptr(partial, f32, 'partial'), _ptr(dw, f32, 'dw'), nblocks, dw.numel(), _stream()),
+        'plm_colsum_accum')
+  return dw
+
+
+# ---------------------------------------------------------------------------------------------- SwiGLU
+def swiglu_fwd(u, h):
+  lib = _lib.load()
+  F = h.shape[-1]
+  rows = h.numel() // F
+  check(lib.plm_swiglu_fwd(_ptr(u, bf16, 'u'), _ptr(h, bf16, 'h'), rows, F, _stream()), 'plm_swiglu_fwd')
+  return h
+
+
+def swiglu_bwd(dh, u, du):
+  lib = _lib.load()
+  F = dh.shape[-1]
+  rows = dh.numel() // F
+  check(lib.plm_swiglu_bwd(_ptr(dh, bf16, 'dh'), _ptr(u, bf16, 'u'), _ptr(du, bf16, 'du'), rows, F, _stream()),
+        'plm_swiglu_bwd')
+  return du
+
+
+# ---------------------------------------------------------------------------------------------- embedding
+def embed_fwd(ids, W, x):
+  lib = _lib.load()
+  vocab, d = W.shape
+  check(lib.plm_embed_fwd(_ptr(ids, torch.int64, 'ids'), _ptr(W, f32, 'W'), _ptr(x, f32, 'x'), ids.numel(), d, vocab,
+                          _stream()), 'plm_embed_fwd')
+  return x
+
+
+def embed_bwd(ids, dx, dW):
+  lib = _lib.load()
+  vocab, d = dW.shape
+  check(lib.plm_embed_bwd(_ptr(ids, torch.int64, 'ids'), _ptr(dx, f32, 'dx'), _ptr(dW, f32, 'dW'), ids.numel(), d,
+                          vocab, _stream()), 'plm_embed_bwd')
+  return dW
+
+
+# ---------------------------------------------------------------------------------------------- cross-entropy
+def ce_fwd_bwd(logits, targets, row_loss, row_lse, stats, V, grad_scale=1.0, write_grad=True):
+  """logits: bf16 [rows, ld>=V]; overwritten with dlogits when write_grad. stats: fp32[4] -> [sum, n_valid, mean]."""
+  lib = _lib.load()
+  rows = logits.shape[0]
+  check(lib.plm_ce_fwd_bwd(_ptr(logits, bf16, 'logits'), _ptr(targets, torch.int64, 'targets'),
+                           _ptr(row_loss, f32, 'row_loss'), _ptr(row_lse, f32, 'row_lse'), _ptr(stats, f32, 'stats'),
+                           rows, V, _rowmajor_ld(logits, 'logits'), float(grad_scale), int(write_grad), _stream()),
+        'plm_ce_fwd_bwd')
+  return stats
+
+
+# ---------------------------------------------------------------------------------------------- optimizer path
+def sumsq(g, workspace, out, accumulate=False):
+  lib = _lib.load()
+  check(lib.plm_sumsq(_ptr(g, f32, 'g'), g.numel(), _ptr(workspace, f32, 'workspace'), _ptr(out, f32, 'out'),
+                      int(accumulate), _stream()), 'plm_sumsq')
+  return out
+
+
+def adamw_step(p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, step, gnorm_sq=None, max_norm=0.0):
+  lib = _lib.load()
+  bc1 = 1.0 - beta1 ** step
+  bc2 = 1.0 - beta2 ** step
+  check(lib.plm_adamw_step(_ptr(p, f32, 'p'), _ptr(g, f32, 'g'), _ptr(m, f32, 'm'), _ptr(v, f32, 'v'),
+                           _ptr(p_bf16, bf16, 'p_bf16'), p.numel(), lr, beta1, beta2, eps, weight_decay, bc1, bc2,
+                           _ptr(gnorm_sq, f32, 'gnorm_sq'), float(max_norm or 0.0), _stream()), 'plm_adamw_step')
+
+
+def signsgd_step(p, g, m, p_bf16, lr, momentum, dampening, weight_decay, first_step, gnorm_sq=None, max_norm=0.0):
+  lib = _lib.load()
+  check(lib.plm_signsgd_step(_ptr(p, f32, 'p'), _ptr(g, f32, 'g'), _ptr(m, f32, 'm'), _ptr(p_bf16, bf16, 'p_bf16'),
+                             p.numel(), lr, momentum, dampening, weight_decay, int(first_step),
+                             _ptr(gnorm_sq, f32, 'gnorm_sq'), float(max_norm or 0.0), _stream()), 'plm_signsgd_step')
+
+
+def cast_f32_bf16(src, dst, scale=1.0):
+  lib = _lib.load()
+  check(lib.plm_cast_f32_bf16(_ptr(src, f32, 'src'), _ptr(dst, bf16, 'dst'), src.numel(), float(scale), _stream()),
+        'plm_cast_f32_bf16')
+  return dst
+
+
+def cast_bf16_f32(src, dst, scale=1.0):
+  lib = _lib.load()
+  check(lib.plm_cast_bf16_f32(_ptr(src, bf16, 'src'), _ptr(dst, f32, 'dst'), src.numel(), float(scale), _stream()),
+        'plm_cast_bf16_f32')
+  return dst
+
+
+def seg_start_from_lengths(lengths, offsets, seg_start, B, T):
+  lib = _lib.load()
+  check(lib.plm_seg_start_from_lengths(_ptr(lengths, torch.int32, 'lengths'), _ptr(offsets, torch.int32, 'offsets'),
+                                       _ptr(seg_start, torch.int32, 'seg_start'), B, T, _stream()),
+        'plm_seg_start_from_lengths')
+  return seg_start
