@@ -125,7 +125,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nq = T / AB_T;
+  const int nq = (T + AB_T - 1) / AB_T;  // ragged tail: T need not be a multiple of 128
   const int j = blockIdx.x;  // key tile
   const int h = blockIdx.y;
   const int b = blockIdx.z;
@@ -245,11 +245,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const int st = it & 1;
       // stage the per-query vectors of this step
       {
+        const bool q_ok = i * AB_T + r < T;
         const int64_t qrow = seq0 + i * AB_T + r;
         const int64_t vidx = (static_cast<int64_t>(b) * H + h) * T + i * AB_T + r;
-        sLse[st * AB_T + r] = lse[vidx] * 1.4426950408889634f;
-        sDelta[st * AB_T + r] = delta[vidx];
-        sSeg[st * AB_T + r] = seg_start ? seg_start[qrow] : 0;
+        sLse[st * AB_T + r] = q_ok ? lse[vidx] * 1.4426950408889634f : 0.f;
+        sDelta[st * AB_T + r] = q_ok ? delta[vidx] : 0.f;
+        sSeg[st * AB_T + r] = q_ok ? (seg_start ? seg_start[qrow] : 0) : 0x7fffffff;  // q >= T: nothing allowed
       }
       named_bar_sync(1, 128);
       const float* lse2 = sLse + st * AB_T;
@@ -323,11 +324,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (it > 0) {
         // dQ of the previous step (overlaps this step's dV/dK MMAs): lane r now means QUERY row r of tile i-1
         float* dst = dq_acc + (seq0 + (i - 1) * AB_T + r) * d + h * AB_HD;
+        const bool dq_ok = (i - 1) * AB_T + r < T;
 #pragma unroll
         for (int c = 0; c < AB_HD / 32; ++c) {
           uint32_t t[32];
           tmem_ld32(tDQ + lane_off + c * 32, t);
           tmem_ld_wait();
+          if (!dq_ok) continue;
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4)
             red_add_f32x4(dst + c * 32 + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
@@ -344,11 +347,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tc_fence_after();
     {
       float* dst = dq_acc + (seq0 + (j + n_it - 1) * AB_T + r) * d + h * AB_HD;
+      const bool dq_ok = (j + n_it - 1) * AB_T + r < T;
 #pragma unroll
       for (int c = 0; c < AB_HD / 32; ++c) {
         uint32_t t[32];
         tmem_ld32(tDQ + lane_off + c * 32, t);
         tmem_ld_wait();
+        if (!dq_ok) continue;
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4)
           red_add_f32x4(dst + c * 32 + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
@@ -362,6 +367,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       uint32_t t[32];
       tmem_ld32(tDV + lane_off + c * 32, t);
       tmem_ld_wait();
+      if (kj >= T) continue;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         uint4 v;
@@ -377,6 +383,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       uint32_t t[32];
       tmem_ld32(tDK + lane_off + c * 32, t);
       tmem_ld_wait();
+      if (kj >= T) continue;
       if (rope) {
         const float4* tab = reinterpret_cast<const float4*>(rope + (static_cast<int64_t>(kj) * (AB_HD >> 1) + c * 16) * 2);
 #pragma unroll
@@ -420,7 +427,6 @@ extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, 
   PLM_REQUIRE(qkv && out && dout && lse && dqkv && delta && dq_acc, "attn_bwd: null pointer");
   PLM_REQUIRE(B > 0 && T > 0 && H > 0, "attn_bwd: bad size");
   if (hd != AB_HD) return fail(PLM_ERR_UNSUPPORTED, "attn_bwd: head_dim %d unsupported (need 64)", hd);
-  if (T % AB_T != 0) return fail(PLM_ERR_UNSUPPORTED, "attn_bwd: seq_len %d must be a multiple of 128", T);
   PLM_REQUIRE(aligned16(qkv) && aligned16(out) && aligned16(dout) && aligned16(dqkv) && aligned16(dq_acc) &&
                   (!rope_table || aligned16(rope_table)),
               "attn_bwd: misaligned pointer");
@@ -452,7 +458,7 @@ extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, 
     if (rc != PLM_OK) return rc;
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
-  dim3 grid(T / AB_T, H, B);
+  dim3 grid((T + AB_T - 1) / AB_T, H, B);
   attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, lse, delta, seg_start, rope_table,
                                                          static_cast<__nv_bfloat16*>(dqkv), dq_acc, T, H, scale,
                                                          scale * 1.4426950408889634f);

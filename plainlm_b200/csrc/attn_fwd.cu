@@ -143,7 +143,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
     const int r = warp * 32 + lane;          // row within the tile == TMEM lane
     const int qi = qt * ATT_BQ + r;          // position within the sequence
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    const int seg_lo = seg_start ? seg_start[row0 + r] : 0;
+    const bool row_ok = qi < T;                // ragged tail: T need not be a multiple of 128
+    const int seg_lo = (seg_start && row_ok) ? seg_start[row0 + r] : 0;
     float m_run = -INFINITY, l_run = 0.f;
 
     for (int it = 0; it < n_it; ++it) {
@@ -236,6 +237,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
       uint32_t t[32];
       tmem_ld32(tO + lane_off + c * 32, t);
       tmem_ld_wait();
+      if (!row_ok) continue;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 v;
@@ -247,7 +249,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
       }
     }
     const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
-    lse[(static_cast<int64_t>(b) * H + h) * T + qi] = (m_use + lg2(l_run)) * 0.6931471805599453f;
+    if (row_ok) lse[(static_cast<int64_t>(b) * H + h) * T + qi] = (m_use + lg2(l_run)) * 0.6931471805599453f;
   }
 
   tc_fence_before();
@@ -267,8 +269,7 @@ extern "C" int plm_attn_fwd(const void* qkv, const int32_t* seg_start, void* out
   PLM_REQUIRE(qkv && out && lse, "attn_fwd: null pointer");
   PLM_REQUIRE(B > 0 && T > 0 && H > 0, "attn_fwd: bad size");
   if (hd != ATT_HD) return fail(PLM_ERR_UNSUPPORTED, "attn_fwd: head_dim %d unsupported (need 64)", hd);
-  if (T % ATT_BQ != 0) return fail(PLM_ERR_UNSUPPORTED, "attn_fwd: seq_len %d must be a multiple of 128", T);
-  PLM_REQUIRE(aligned16(qkv) && aligned16(out), "attn_fwd: misaligned pointer");
+    PLM_REQUIRE(aligned16(qkv) && aligned16(out), "attn_fwd: misaligned pointer");
   PLM_REQUIRE(static_cast<int64_t>(B) * T < (1ll << 31) && B <= 65535 && H <= 65535, "attn_fwd: size too large");
 
   static std::once_flag once;
@@ -283,7 +284,7 @@ extern "C" int plm_attn_fwd(const void* qkv, const int32_t* seg_start, void* out
   int rc = make_tmap_bf16_2d(&tm, qkv, static_cast<uint64_t>(B) * T, 3ull * d, 3ull * d, ATT_BK, 64);
   if (rc != PLM_OK) return rc;
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(hd));
-  dim3 grid(T / ATT_BQ, H, B);
+  dim3 grid((T + ATT_BQ - 1) / ATT_BQ, H, B);
   attn_fwd_kernel<<<grid, ATT_THREADS, ATT_FWD_SMEM, stream>>>(tm, seg_start, static_cast<__nv_bfloat16*>(out), lse, T,
                                                                H, scale_log2);
   return check_launch("attn_fwd");

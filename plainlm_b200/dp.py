@@ -1,0 +1,74 @@
+"""Data-parallel gradient exchange: bucketed bf16 all-reduce over NCCL, overlapped with backward.
+
+Replaces torch DDP as wrapped at engine/engine.py:64-65 of the reference (fp32 all-reduce of ~25 MiB buckets in
+reverse registration order, divide by world size, sync only on the last micro-step, engine.py:104-105).  Here the
+buckets are contiguous ranges of the model's flat fp32 gradient buffer, in the order backward finalises them
+(lm_head, layer L-1 .. layer 0, embedding, norm weights).  When the runtime reports bucket i final, the comm stream
+  1. waits for the compute stream's event,
+  2. packs the range to bf16 pre-scaled by 1/world  (plm_cast_f32_bf16),
+  3. all-reduces it (NCCL SUM over NVLink/NVSwitch, torch.distributed is only the plumbing),
+  4. unpacks back into the fp32 gradient range       (plm_cast_bf16_f32),
+while the compute stream keeps running the rest of backward.  `finish()` joins the streams before clipping.
+"""
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def broadcast_parameters(flat, src=0, group=None):
+  """Make every rank start from rank `src`'s weights (what the DDP constructor does, engine.py:65): ranks seed
+  their RNG with seed+rank (torch_utils.py:35-37), so their initialisations differ."""
+  dist.broadcast(flat.params, src=src, group=group)
+  flat.refresh_shadow()
+
+
+class GradReducer:
+  def __init__(self, flat, group=None, wire_dtype=torch.bfloat16, pack=None, unpack=None):
+    """pack(src_f32, dst_wire, scale) / unpack(src_wire, dst_f32, scale) default to the CUDA cast kernels; the CPU
+    (gloo) unit tests inject torch casts to exercise the bucket logic without a GPU."""
+    self.flat = flat
+    self.group = group
+    self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+    self.buckets = list(flat.buckets)
+    self.wire = torch.empty(flat.total, device=flat.grads.device, dtype=wire_dtype)
+    self.wire_dtype = wire_dtype
+    self.on_cuda = flat.grads.is_cuda
+    self.pack = pack or (lambda s, d, sc: ops.cast_f32_bf16(s, d, sc))
+    self.unpack = unpack or (lambda s, d, sc: ops.cast_bf16_f32(s, d, sc))
+    if wire_dtype == torch.float32:  # A/B switch: the reference's fp32 wire format
+      self.pack = lambda s, d, sc: d.copy_(s).mul_(sc)
+      self.unpack = lambda s, d, sc: d.copy_(s)
+    self.comm_stream = torch.cuda.Stream(device=flat.grads.device) if self.on_cuda else None
+    self._pending = []
+    self.launched = 0
+
+  def bucket_ready(self, i):
+    """Called by the runtime right after the launches that finalise bucket i (last micro-step only)."""
+    if self.world == 1:
+      return
+    a, b = self.buckets[i]
+    g = self.flat.grads[a:b]
+    w = self.wire[a:b]
+    if self.on_cuda:
+      ev = torch.cuda.Event()
+      ev.record(torch.cuda.current_stream())
+      with torch.cuda.stream(self.comm_stream):
+        self.comm_stream.wait_event(ev)
+        self.pack(g, w, 1.0 / self.world)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM, group=self.group)
+        self.unpack(w, g, 1.0)
+    else:
+      self.pack(g, w, 1.0 / self.world)
+      dist.all_reduce(w, op=dist.ReduceOp.SUM, group=self.group)
+      self.unpack(w, g, 1.0)
+    self.launched += 1
+
+  def finish(self):
+    """Join: later work on the compute stream (grad-norm, optimizer) sees the reduced gradients."""
+    if self.world == 1 or not self.on_cuda:
+      return
+    ev = torch.cuda.Event()
+    ev.record(self.comm_stream)
+    torch.cuda.current_stream().wait_event(ev)

@@ -1,0 +1,207 @@
+"""TorchEngine: one training micro-step on the B200 kernels (reference: engine/engine.py).
+
+Same constructor, attributes (.model .optimizer .scheduler .scaler .micro_steps) and `step(batch)` / `eval(loader)`
+contract as the reference, so the reference's train.py, utils.log and checkpoint_utils.py drive it unchanged.
+What changes underneath (SURVEY.md §3.2 -> here):
+  * fwd + loss + bwd is ONE hand-scheduled kernel sequence (models/runtime.py): no autocast, no autograd graph,
+    no dense (B,T,T) mask — document masking travels as int32 segment starts;
+  * DDP is replaced by a bucketed bf16 all-reduce overlapped with backward (dp.py), only on the last micro-step
+    of an accumulation cycle (reference: engine.py:104-105);
+  * clip_grad_norm_ + optimizer.step() is one reduction pass + one flat update kernel, clip coefficient computed on
+    the device (no host sync);
+  * the per-micro-step `isnan` host sync (reference: engine.py:116) is kept in meaning but deferred: the loss is
+    copied to pinned memory asynchronously and checked at the next call (or by `check_nan()`).
+"""
+
+import torch
+from torch import distributed as dist
+
+from ..data_utils import seg_start_from_docs_lengths
+from ..dp import GradReducer, broadcast_parameters
+from ..models import get_param_groups
+from ..optim import intialize_optimizer, initialize_scheduler
+from ..optim.flat import GradClip, grad_sumsq, sumsq_workspace
+
+
+class _HostStaging:
+  """Double-buffered pinned staging for the per-step host->device copies (reference: engine.py:27-30 pins and copies
+  synchronously on the main thread every micro-step)."""
+
+  def __init__(self, device, slots=2):
+    self.device = device
+    self.slots = slots
+    self.k = 0
+    self.bufs = {}
+
+  def put(self, name, cpu_tensor):
+    key = (name, self.k, tuple(cpu_tensor.shape), cpu_tensor.dtype)
+    rec = self.bufs.get(key)
+    if rec is None:
+      pinned = torch.empty(cpu_tensor.shape, dtype=cpu_tensor.dtype, pin_memory=True)
+      dev = torch.empty(cpu_tensor.shape, dtype=cpu_tensor.dtype, device=self.device)
+      rec = [pinned, dev, None]
+      self.bufs[key] = rec
+    pinned, dev, ev = rec
+    if ev is not None:
+      ev.synchronize()  # the copy that last used this slot finished long ago; cheap guard
+    pinned.copy_(cpu_tensor)
+    dev.copy_(pinned, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    rec[2] = ev
+    return dev
+
+  def advance(self):
+    self.k = (self.k + 1) % self.slots
+
+
+class TorchEngine(torch.nn.Module):
+  """A module containing model, optimizer, scheduler, grad scaler; wraps a training step with grad accumulation."""
+
+  def __init__(self, model, cfg, device, local_rank, ckpt):
+    super().__init__()
+    self.micro_steps = 0
+    self.accumulated_samples = 0
+    self.seq_len = cfg.seq_len
+    self.accumulation_steps = cfg.grad_accumulation_steps
+    self.grad_clip = cfg.grad_clip
+    self.dtype = cfg.dtype
+    self.intra_doc_masking = getattr(cfg, 'intra_doc_masking', False)
+    self.device = device
+    if 'cuda' not in str(device):
+      raise RuntimeError('plainlm_b200.TorchEngine needs a CUDA device (B200); there is no CPU path')
+    if self.dtype != 'bfloat16':
+      raise NotImplementedError(
+        f"dtype '{self.dtype}': the B200 kernels implement the bfloat16 policy (bf16 GEMM operands, fp32 accumulation, "
+        'fp32 master weights); float16+GradScaler / float32 are SURVEY.md §8(f) N4'
+      )
+
+    if cfg.resume:
+      model.load_state_dict(ckpt['state_dict'])
+      self.micro_steps = ckpt['step'] * cfg.grad_accumulation_steps
+
+    self.model = model.to(device)
+    self.rt = self.model.runtime()
+    self.reducer = None
+    if dist.is_initialized():
+      broadcast_parameters(self.rt.flat)
+      wire = torch.float32 if getattr(cfg, 'ddp_fp32_allreduce', False) else torch.bfloat16
+      self.reducer = GradReducer(self.rt.flat, wire_dtype=wire)
+
+    # bf16 needs no loss scaling; a disabled scaler keeps checkpoint_utils.py's 'scaler' entry round-tripping
+    self.scaler = torch.amp.GradScaler(enabled=False)
+
+    param_groups = get_param_groups(model, cfg.weight_decay)
+    self.optimizer = intialize_optimizer(param_groups, cfg)
+    self.scheduler = initialize_scheduler(self.optimizer, cfg)
+    if cfg.resume:
+      self.optimizer.load_state_dict(ckpt['optimizer'])
+      self.scheduler.load_state_dict(ckpt['scheduler'])
+      self.scaler.load_state_dict(ckpt['scaler'])
+
+    dev = self.rt.flat.params.device
+    self._staging = _HostStaging(dev)
+    self._sumsq_ws = sumsq_workspace(dev)
+    self._gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+    self._loss_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
+    self._loss_events = [None, None]
+    self._loss_slot = 0
+
+  # ------------------------------------------------------------------------------------------ batch staging
+  def _move_to_device(self, batch):
+    """reference: engine.py:13-34.  Slicing is done on the host (bit-exact integers), the dense mask is replaced by
+    int32 segment starts built from `docs_lengths`."""
+    ids = batch['input_ids']
+    T = self.seq_len
+    seg = None
+    if ids.is_cuda:
+      inputs, targets = ids[:, :T].contiguous(), ids[:, 1 : T + 1].contiguous()
+      if self.intra_doc_masking:
+        seg = seg_start_from_docs_lengths(batch['docs_lengths'], T).to(ids.device).reshape(-1)
+      return inputs, targets, seg
+    inputs = self._staging.put('inputs', ids[:, :T])
+    targets = self._staging.put('targets', ids[:, 1 : T + 1])
+    if self.intra_doc_masking:
+      seg = self._staging.put('seg', seg_start_from_docs_lengths(batch['docs_lengths'], T)).reshape(-1)
+    self._staging.advance()
+    return inputs, targets, seg
+
+  # ------------------------------------------------------------------------------------------ NaN guard
+  def _record_loss(self, loss):
+    k = self._loss_slot
+    self._loss_host[k : k + 1].copy_(loss.reshape(1), non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    self._loss_events[k] = ev
+    self._loss_slot = 1 - k
+
+  def check_nan(self, wait=False):
+    """Raise ValueError('Train loss is nan') (reference: engine.py:116-117) for any completed micro-step."""
+    for k, ev in enumerate(self._loss_events):
+      if ev is None:
+        continue
+      if wait:
+        ev.synchronize()
+      if ev.query():
+        self._loss_events[k] = None
+        if torch.isnan(self._loss_host[k]):
+          raise ValueError('Train loss is nan')
+
+  # ------------------------------------------------------------------------------------------ train step
+  def step(self, batch):
+    """Wraps a fwd pass, bwd pass, and (at the accumulation boundary) an optimization step."""
+    inputs, targets, seg = self._move_to_device(batch)
+    return self.step_device(inputs, targets, seg)
+
+  def step_device(self, inputs, targets, seg_start=None):
+    """Same as step() for a micro-batch already on the device (int64 [B,T] inputs / targets, int32 [B*T] segments)."""
+    self.model.train()
+    self.check_nan()
+    self.micro_steps += 1
+    self.accumulated_samples += 1
+    if self.accumulated_samples == 1:
+      self.rt.flat.zero_grads()
+    last = self.accumulated_samples == self.accumulation_steps
+    on_bucket = self.reducer.bucket_ready if (self.reducer is not None and last) else None
+
+    loss_val = self.rt.loss_and_backward(inputs, targets, seg, grad_scale=1.0 / self.accumulation_steps,
+                                         backward=True, on_bucket=on_bucket)
+    self._record_loss(loss_val)
+
+    if last:
+      self.accumulated_samples = 0
+      if self.reducer is not None:
+        self.reducer.finish()
+      clip = None
+      if self.grad_clip:
+        grad_sumsq(self.rt.flat, self._sumsq_ws, self._gnorm_sq)
+        clip = GradClip(self._gnorm_sq, self.grad_clip)
+      self.optimizer.step(grad_clip=clip)
+      if self.scheduler:
+        self.scheduler.step()
+    return loss_val
+
+  def grad_norm(self):
+    """Total gradient L2 norm of the last optimizer step (device tensor; what clip_grad_norm_ returns)."""
+    return self._gnorm_sq.sqrt()
+
+  # ------------------------------------------------------------------------------------------ eval
+  @torch.no_grad()
+  def eval(self, dataloader):
+    """reference: engine.py:143-177, with the loss-only fused forward (and without the reference's `.item()` crash on
+    a float, engine.py:175)."""
+    self.model.eval()
+    total = torch.zeros(1, device=self.rt.flat.params.device, dtype=torch.float32)
+    num_batches = 0
+    for batch in dataloader:
+      inputs, targets, seg = self._move_to_device(batch)
+      loss = self.rt.loss_and_backward(inputs, targets, seg, backward=False)
+      total += loss
+      num_batches += 1
+    count = torch.tensor([float(num_batches)], device=total.device)
+    if dist.is_initialized():
+      dist.all_reduce(total, op=dist.ReduceOp.SUM)
+      dist.all_reduce(count, op=dist.ReduceOp.SUM)
+    if torch.isnan(total).item():
+      raise ValueError('Validation loss is nan')
+    return (total / count).item()

@@ -1,0 +1,264 @@
+"""Hand-scheduled forward/backward of the whole Transformer on the CUDA kernels — the fused training path.
+
+Replaces, for one micro-batch, everything between engine/engine.py:108 and :120 of the reference:
+  model(inputs, attn_mask) -> CrossEntropyLoss -> loss / accum -> backward()
+with a fixed sequence of kernel launches over pre-allocated activation buffers.  No autograd graph, no allocator
+traffic, no dtype-cast kernels: bf16 weight shadows are persistent (refreshed by the optimizer kernel), gradients are
+accumulated straight into the flat fp32 .grad buffer by the wgrad GEMM epilogue, and the dense attention mask of the
+reference is replaced by int32 segment starts.
+
+Layout in HBM (M = B*T tokens, d model dim, F GLU hidden, V vocab):
+  params / grads  flat fp32 in data-parallel bucket order [lm_head | layer L-1 .. layer 0 | embed | all norm weights]
+  shadows         flat bf16, same order (GEMM B operands)
+  per layer saved x_in fp32[M,d], h1 bf16[M,d], rstd1[M], qkv bf16[M,3d], attn bf16[M,d], lse[B,H,T],
+                  x_mid fp32[M,d], h2 bf16[M,d], rstd2[M], u bf16[M,2F], g bf16[M,F]
+"""
+
+import torch
+
+from .. import _lib, ops
+
+bf16, f32 = torch.bfloat16, torch.float32
+_ALIGN = 64  # elements; keeps every parameter view 256-byte aligned
+
+
+def _bucket_param_names(model):
+  """Flat order = order in which gradients become final during backward (DDP reverse-registration order analogue)."""
+  L = model.n_layers
+  tied = model.lm_head.weight is model.embed_tokens.weight
+  buckets = [] if tied else [['lm_head.weight']]  # tied: the shared matrix is final only after the embedding backward
+  for i in reversed(range(L)):
+    pre = f'layers.{i}.'
+    buckets.append([pre + 'mlp.fc2.weight', pre + 'mlp.fc1.weight', pre + 'attn.w_out.weight', pre + 'attn.w_qkv.weight'])
+  buckets.append(['embed_tokens.weight'])
+  norms = ['out_norm.weight']
+  for i in reversed(range(L)):
+    norms += [f'layers.{i}.mlp_norm.weight', f'layers.{i}.attn_norm.weight']
+  buckets.append(norms)
+  return buckets
+
+
+class FlatParams:
+  """Re-homes every parameter of the model as a view into one flat fp32 buffer (plus flat grads and bf16 shadows).
+
+  state_dict names, shapes and dtypes are unchanged (checkpoint_utils.py of the reference keeps working); the flat
+  buffers and shadows are not registered as buffers and never appear in a state_dict.
+  """
+
+  def __init__(self, model, device):
+    named = dict(model.named_parameters(remove_duplicate=False))
+    seen = {}
+    self.entries = []  # (name, param, offset, numel)
+    self.buckets = []  # (start, end) element ranges
+    off = 0
+    for names in _bucket_param_names(model):
+      start = off
+      for n in names:
+        p = named[n]
+        if id(p) in seen:  # tied weights: one storage, one gradient
+          continue
+        seen[id(p)] = n
+        self.entries.append((n, p, off, p.numel()))
+        off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+      if off > start:
+        self.buckets.append((start, off))
+    self.norm_start = self.buckets[-1][0]
+    self.total = off
+    missing = [n for n, p in named.items() if id(p) not in seen]
+    if missing:
+      raise RuntimeError(f'plainlm_b200: parameters without a flat slot: {missing}')
+    self.params = torch.zeros(off, device=device, dtype=f32)
+    self.grads = torch.zeros(off, device=device, dtype=f32)
+    self.shadow = torch.zeros(off, device=device, dtype=bf16)
+    for n, p, o, k in self.entries:
+      view = self.params[o : o + k].view(p.shape)
+      view.copy_(p.data.to(device=device, dtype=f32))
+      p.data = view
+      p.grad = self.grads[o : o + k].view(p.shape)
+      p._plm_shadow = self.shadow[o : o + k].view(p.shape)
+      p._plm_flat = (self, o, k)
+    self.refresh_shadow()
+    self._versions = self._version_sum()
+
+  def _version_sum(self):
+    return sum(p._version for _, p, _, _ in self.entries)
+
+  def refresh_shadow(self):
+    ops.cast_f32_bf16(self.params, self.shadow)
+
+  def refresh_if_stale(self):
+    """Parameters changed behind our back (load_state_dict, a foreign optimizer): re-cast the bf16 shadows.
+    Our own optimizer kernels write the shadows themselves and do not bump autograd version counters."""
+    v = self._version_sum()
+    if v != self._versions:
+      self.refresh_shadow()
+      self._versions = v
+
+  def restore_grad_views(self):
+    for n, p, o, k in self.entries:
+      if p.grad is None or p.grad.data_ptr() != self.grads.data_ptr() + 4 * o:
+        p.grad = self.grads[o : o + k].view(p.shape)
+
+  def zero_grads(self):
+    self.grads.zero_()
+
+
+class _Workspace:
+  def __init__(self, rt, B, T):
+    m = rt.model
+    dev = rt.flat.params.device
+    M, d, F, V, H, L = B * T, m.dim, m.hidden_dim, m.vocab_size, m.n_heads, m.n_layers
+    e = lambda *shape, dtype=bf16: torch.empty(*shape, device=dev, dtype=dtype)  # noqa: E731
+    self.B, self.T, self.M = B, T, M
+    self.x = [e(M, d, dtype=f32) for _ in range(L + 1)]      # x[l] = input of layer l; x[L] = final stream
+    self.x_mid = [e(M, d, dtype=f32) for _ in range(L)]
+    self.h1 = [e(M, d) for _ in range(L)]
+    self.h2 = [e(M, d) for _ in range(L)]
+    self.rstd1 = [e(M, dtype=f32) for _ in range(L)]
+    self.rstd2 = [e(M, dtype=f32) for _ in range(L)]
+    self.qkv = [e(M, 3 * d) for _ in range(L)]
+    self.attn = [e(M, d) for _ in range(L)]
+    self.lse = [e(B, H, T, dtype=f32) for _ in range(L)]
+    self.u = [e(M, 2 * F) for _ in range(L)]
+    self.g = [e(M, F) for _ in range(L)]
+    self.hf = e(M, d)
+    self.rstd_f = e(M, dtype=f32)
+    self.logits = e(M, V)
+    self.row_loss = e(M, dtype=f32)
+    self.row_lse = e(M, dtype=f32)
+    self.stats = torch.zeros(4, device=dev, dtype=f32)
+    # backward temporaries
+    self.dx = e(M, d, dtype=f32)
+    self.dx_b = e(M, d)
+    self.dh = e(M, d)
+    self.dg = e(M, F)
+    self.du = e(M, 2 * F)
+    self.dattn = e(M, d)
+    self.dqkv = e(M, 3 * d)
+    self.delta = e(B, H, T, dtype=f32)
+    self.dq_acc = e(M, d, dtype=f32)
+    self.nblk = ops.rmsnorm_bwd_blocks(M)
+    self.dw_part = e(self.nblk, d, dtype=f32)
+
+
+class TrainRuntime:
+  """Owns the flat parameter storage and activation workspaces of one Transformer and runs its train step."""
+
+  def __init__(self, model, device):
+    self.model = model
+    self.flat = FlatParams(model, device)
+    self.device = device
+    self._ws = {}
+    self.rope = model.rope_table(device)
+    p = dict(model.named_parameters(remove_duplicate=False))
+    L = model.n_layers
+    sh = lambda n: p[n]._plm_shadow  # noqa: E731
+    gr = lambda n: p[n].grad  # noqa: E731
+    self.names = p
+    self.tied = model.lm_head.weight is model.embed_tokens.weight
+    self.W = {n: sh(n) for n in p}   # bf16 GEMM operands
+    self.G = {n: gr(n) for n in p}   # fp32 grad views
+    self.P = {n: p[n].data for n in p}
+    self.L = L
+
+  def workspace(self, B, T):
+    key = (B, T)
+    if key not in self._ws:
+      if len(self._ws) >= 2:  # keep at most two shapes alive (train + eval)
+        self._ws.pop(next(iter(self._ws)))
+      self._ws[key] = _Workspace(self, B, T)
+    return self._ws[key]
+
+  # ------------------------------------------------------------------------------------------ forward
+  def forward_hidden(self, ids, seg_start, ws):
+    """Embedding + all blocks + final norm. Fills ws (saved activations); returns ws.hf (bf16 [M,d])."""
+    m = self.model
+    B, T, d, H, hd, L = ws.B, ws.T, m.dim, m.n_heads, m.head_dim, self.L
+    W, P = self.W, self.P
+    ops.embed_fwd(ids.reshape(-1), P['embed_tokens.weight'], ws.x[0])
+    for l in range(L):
+      pre = f'layers.{l}.'
+      ops.rmsnorm_fwd(ws.x[l], P[pre + 'attn_norm.weight'], ws.h1[l], ws.rstd1[l], m.eps)
+      ops.gemm(ws.h1[l], W[pre + 'attn.w_qkv.weight'], ws.qkv[l], epilogue=_lib.EPI_BF16_ROPE, rope_table=self.rope,
+               rope_cols=2 * d, rope_T=T, head_dim=hd)
+      ops.attn_fwd(ws.qkv[l], ws.attn[l], ws.lse[l], B, T, H, hd, seg_start=seg_start)
+      ops.gemm(ws.attn[l], W[pre + 'attn.w_out.weight'], ws.x_mid[l], epilogue=_lib.EPI_RESID_F32, residual=ws.x[l])
+      ops.rmsnorm_fwd(ws.x_mid[l], P[pre + 'mlp_norm.weight'], ws.h2[l], ws.rstd2[l], m.eps)
+      ops.gemm(ws.h2[l], W[pre + 'mlp.fc1.weight'], ws.u[l])
+      ops.swiglu_fwd(ws.u[l], ws.g[l])
+      ops.gemm(ws.g[l], W[pre + 'mlp.fc2.weight'], ws.x[l + 1], epilogue=_lib.EPI_RESID_F32, residual=ws.x_mid[l])
+    ops.rmsnorm_fwd(ws.x[L], P['out_norm.weight'], ws.hf, ws.rstd_f, m.eps)
+    return ws.hf
+
+  def forward_logits(self, ids, seg_start, ws):
+    self.forward_hidden(ids, seg_start, ws)
+    ops.gemm(ws.hf, self.W['lm_head.weight'], ws.logits)
+    return ws.logits
+
+  # ------------------------------------------------------------------------------------------ loss + backward
+  def loss_and_backward(self, ids, targets, seg_start=None, grad_scale=1.0, backward=True, on_bucket=None):
+    """One micro-batch: returns the mean CE loss (0-dim device tensor, un-scaled); when `backward`, accumulates
+    d(loss * grad_scale)/dparams into the flat grad buffer.  `on_bucket(i)` is called right after the launches that
+    finalise gradient bucket i (data-parallel overlap hook)."""
+    self.flat.refresh_if_stale()
+    B, T = ids.shape
+    ws = self.workspace(B, T)
+    self.forward_logits(ids, seg_start, ws)
+    m = self.model
+    ops.ce_fwd_bwd(ws.logits, targets.reshape(-1), ws.row_loss, ws.row_lse, ws.stats, m.vocab_size,
+                   grad_scale=grad_scale, write_grad=backward)
+    loss = ws.stats[2].clone()
+    if backward:
+      self.backward_from_dlogits(ids, seg_start, ws, on_bucket)
+    return loss
+
+  def _wgrad(self, dy, x, name):
+    """grad[name] += dy^T x  (contraction over tokens, both operands read in place as MN-major)."""
+    ops.gemm(dy, x, self.G[name], a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ATOMIC_F32, splits=0)
+
+  def _dgrad(self, dy, name, out):
+    """out = dy W[name]  (W read in place as an MN-major B operand)."""
+    ops.gemm(dy, self.W[name], out, a_kmajor=True, b_kmajor=False)
+
+  def backward_from_dlogits(self, ids, seg_start, ws, on_bucket=None):
+    m = self.model
+    B, T, H, hd, L = ws.B, ws.T, m.n_heads, m.head_dim, self.L
+    P, G = self.P, self.G
+    bucket = 0
+
+    def done():
+      nonlocal bucket
+      if on_bucket is not None:
+        on_bucket(bucket)
+      bucket += 1
+
+    dlogits = ws.logits  # overwritten in place by the CE kernel
+    self._dgrad(dlogits, 'lm_head.weight', ws.dh)
+    self._wgrad(dlogits, ws.hf, 'lm_head.weight')
+    if not self.tied:
+      done()
+    ops.rmsnorm_bwd(ws.dh, ws.x[L], P['out_norm.weight'], ws.rstd_f, None, ws.dx, ws.dx_b, ws.dw_part)
+    ops.colsum_accum(ws.dw_part, G['out_norm.weight'], ws.nblk)
+    for l in reversed(range(L)):
+      pre = f'layers.{l}.'
+      # ---- MLP branch: x[l+1] = x_mid + fc2(silu(a) * z)
+      self._dgrad(ws.dx_b, pre + 'mlp.fc2.weight', ws.dg)
+      self._wgrad(ws.dx_b, ws.g[l], pre + 'mlp.fc2.weight')
+      ops.swiglu_bwd(ws.dg, ws.u[l], ws.du)
+      self._dgrad(ws.du, pre + 'mlp.fc1.weight', ws.dh)
+      self._wgrad(ws.du, ws.h2[l], pre + 'mlp.fc1.weight')
+      ops.rmsnorm_bwd(ws.dh, ws.x_mid[l], P[pre + 'mlp_norm.weight'], ws.rstd2[l], ws.dx, ws.dx, ws.dx_b, ws.dw_part)
+      ops.colsum_accum(ws.dw_part, G[pre + 'mlp_norm.weight'], ws.nblk)
+      # ---- attention branch: x_mid = x[l] + w_out(attn(rope(w_qkv(h1))))
+      self._dgrad(ws.dx_b, pre + 'attn.w_out.weight', ws.dattn)
+      self._wgrad(ws.dx_b, ws.attn[l], pre + 'attn.w_out.weight')
+      ops.attn_bwd(ws.qkv[l], ws.attn[l], ws.dattn, ws.lse[l], ws.dqkv, ws.delta, ws.dq_acc, B, T, H, hd,
+                   seg_start=seg_start, rope_table=self.rope)
+      self._dgrad(ws.dqkv, pre + 'attn.w_qkv.weight', ws.dh)
+      self._wgrad(ws.dqkv, ws.h1[l], pre + 'attn.w_qkv.weight')
+      done()
+      ops.rmsnorm_bwd(ws.dh, ws.x[l], P[pre + 'attn_norm.weight'], ws.rstd1[l], ws.dx, ws.dx, ws.dx_b, ws.dw_part)
+      ops.colsum_accum(ws.dw_part, G[pre + 'attn_norm.weight'], ws.nblk)
+    ops.embed_bwd(ids.reshape(-1), ws.dx, G['embed_tokens.weight'])
+    done()  # embedding bucket
+    done()  # norm-weight bucket

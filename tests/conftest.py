@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+os.environ.setdefault('TORCHDYNAMO_DISABLE', '1')
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+  config.addinivalue_line('markers', 'gpu: needs a B200 (run with -m gpu under gpurun)')
+
+
+@pytest.fixture(scope='session')
+def golden_dir():
+  return GOLDEN
+
+
+def assert_close(got, ref, rtol, atol=0.0, what=''):
+  """|got - ref| <= atol + rtol * max|ref|  (tolerance relative to the tensor's scale, as for bf16 kernels)."""
+  import torch
+
+  got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+  assert got.shape == ref.shape, f'{what}: shape {tuple(got.shape)} vs {tuple(ref.shape)}'
+  assert not torch.isnan(got).any(), f'{what}: NaN in result'
+  scale = ref.abs().max().item()
+  err = (got - ref).abs().max().item()
+  assert err <= atol + rtol * scale, f'{what}: max err {err:.3e} > {atol:.1e} + {rtol:.1e} * {scale:.3e}'

@@ -267,6 +267,22 @@ def gen_optim_fixture():
   print('optim.pt ok', out['adamw']['state_keys'], out['signsgd']['state_keys'])
 
 
+def gen_init_fixture():
+  """Weights the reference draws for seed 100 (config/*.yaml `seed: 100`): same constructors + same registration
+  order must give the same tensors in plainlm_b200.models.Transformer."""
+  from models import construct_model
+
+  Cfg = namedtuple('Cfg', TINY.keys())
+  torch.manual_seed(100)
+  model, _ = construct_model(Cfg(**TINY))
+  sd = model.state_dict()
+  out = {k: {'sum': float(v.double().sum()), 'abs': float(v.double().abs().sum()), 'head': v.flatten()[:8].tolist()}
+         for k, v in sd.items()}
+  with open(os.path.join(HERE, 'init_seed100.json'), 'w') as f:
+    json.dump(out, f)
+  print('init_seed100.json ok')
+
+
 def gen_misc_fixture():
   from optim.lr_schedule import WarmupCosine
   from torch.utils.data import DistributedSampler
@@ -296,3 +312,4 @@ if __name__ == '__main__':
   gen_engine_fixture()
   gen_optim_fixture()
   gen_misc_fixture()
+  gen_init_fixture()
