@@ -164,7 +164,7 @@ class TorchEngine(torch.nn.Module):
     last = self.accumulated_samples == self.accumulation_steps
     on_bucket = self.reducer.bucket_ready if (self.reducer is not None and last) else None
 
-    loss_val = self.rt.loss_and_backward(inputs, targets, seg, grad_scale=1.0 / self.accumulation_steps,
+    loss_val = self.rt.loss_and_backward(inputs, targets, seg_start, grad_scale=1.0 / self.accumulation_steps,
                                          backward=True, on_bucket=on_bucket)
     self._record_loss(loss_val)
 

@@ -213,3 +213,78 @@ def seg_start_from_lengths(lengths, offsets, seg_start, B, T):
                                        _ptr(seg_start, torch.int32, 'seg_start'), B, T, _stream()),
         'plm_seg_start_from_lengths')
   return seg_start
+
+
+# ---------------------------------------------------------------------------------------------- instrumentation
+# Launch accounting and optional per-call CUDA-event timing, used by bench.py (roofline of the dominant kernel,
+# `gpu_launches`).  Counting is always on (an integer add per call); event timing only when a Profiler is installed.
+KERNELS_PER_CALL = {
+  'gemm': 1, 'attn_fwd': 1, 'attn_bwd': 3, 'rope_qk_': 1, 'rmsnorm_fwd': 1, 'rmsnorm_bwd': 1, 'colsum_accum': 1,
+  'swiglu_fwd': 1, 'swiglu_bwd': 1, 'embed_fwd': 1, 'embed_bwd': 1, 'ce_fwd_bwd': 3, 'sumsq': 2, 'adamw_step': 1,
+  'signsgd_step': 1, 'cast_f32_bf16': 1, 'cast_bf16_f32': 1, 'seg_start_from_lengths': 1,
+}  # fmt: skip
+LAUNCHES = 0
+
+
+class Profiler:
+  """Records (op name, tag, cuda start/end events) for every op call while installed."""
+
+  def __init__(self):
+    self.records = []
+
+  def summary(self):
+    torch.cuda.synchronize()
+    out = {}
+    for name, tag, e0, e1 in self.records:
+      rec = out.setdefault((name, tag), [0, 0.0])
+      rec[0] += 1
+      rec[1] += e0.elapsed_time(e1)
+    return out
+
+
+_profiler = None
+
+
+def _describe(name, args, kwargs):
+  """Shape tag used to group calls of the same kernel and to compute algorithmic work."""
+  if name == 'gemm':
+    a, b = args[0], args[1]
+    ak, bk = kwargs.get('a_kmajor', True), kwargs.get('b_kmajor', True)
+    M, K = (a.shape[0], a.shape[1]) if ak else (a.shape[1], a.shape[0])
+    N = b.shape[0] if bk else b.shape[1]
+    return (M, N, K, int(ak), int(bk), kwargs.get('epilogue', 0))
+  if name in ('attn_fwd', 'attn_bwd'):
+    idx = 3 if name == 'attn_fwd' else 7
+    return tuple(args[idx : idx + 4]) + (kwargs.get('seg_start') is not None,)
+  sizes = tuple(int(t.numel()) for t in args if torch.is_tensor(t))
+  return sizes[:2]
+
+
+def _instrument(name, fn):
+  k = KERNELS_PER_CALL[name]
+
+  def wrapped(*args, **kwargs):
+    global LAUNCHES
+    LAUNCHES += k
+    prof = _profiler
+    if prof is None:
+      return fn(*args, **kwargs)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn(*args, **kwargs)
+    e1.record()
+    prof.records.append((name, _describe(name, args, kwargs), e0, e1))
+    return out
+
+  wrapped.__name__ = name
+  wrapped.__doc__ = fn.__doc__
+  return wrapped
+
+
+for _name in KERNELS_PER_CALL:
+  globals()[_name] = _instrument(_name, globals()[_name])
+
+
+def set_profiler(prof):
+  global _profiler
+  _profiler = prof
