@@ -9,7 +9,7 @@
 namespace plm {
 
 constexpr int NORM_WARPS = 8;
-constexpr int NORM_BWD_MAX_BLOCKS = 296;  // 2 per SM
+constexpr int NORM_BWD_MAX_BLOCKS = 592;  // 4 per SM x 8 warps: enough loads in flight to saturate HBM
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -131,13 +131,29 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
   }
 }
 
-// dw[c] += sum_b partial[b, c], fixed order.
-__global__ void colsum_accum_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nblocks, int d) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
-  float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += partial[static_cast<int64_t>(b) * d + c];
-  dw[c] += s;
+// dw[c] += sum_b partial[b, c].  Block = 32 columns x 8 row groups; fixed summation order => deterministic.
+__global__ void __launch_bounds__(256)
+colsum_accum_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nblocks, int d) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < d) {
+    int b = ty;
+    for (; b + 8 < nblocks; b += 16) {
+      s0 += partial[static_cast<int64_t>(b) * d + c];
+      s1 += partial[static_cast<int64_t>(b + 8) * d + c];
+    }
+    if (b < nblocks) s0 += partial[static_cast<int64_t>(b) * d + c];
+  }
+  red[ty][tx] = s0 + s1;
+  __syncthreads();
+  if (ty == 0 && c < d) {
+    float s = red[0][tx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) s += red[k][tx];
+    dw[c] += s;
+  }
 }
 
 static int norm_bwd_blocks(int64_t rows) {
@@ -204,7 +220,7 @@ int plm_colsum_accum(const float* partial, float* dw, int32_t nblocks, int32_t d
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PLM_REQUIRE(partial && dw && nblocks > 0 && d > 0, "colsum_accum: bad argument");
-  colsum_accum_kernel<<<(d + 127) / 128, 128, 0, stream>>>(partial, dw, nblocks, d);
+  colsum_accum_kernel<<<(d + 31) / 32, 256, 0, stream>>>(partial, dw, nblocks, d);
   return check_launch("colsum_accum");
 }
 
