@@ -1,8 +1,9 @@
 // Flash-attention backward on tcgen05 (backward of models/transformer.py:53-63, reached from engine/engine.py:120).
 //
 // One CTA per (128-key tile j, head, batch), looping over the query tiles i >= j that can see it. 160 threads:
-//   warps 0..3  compute: thread r owns key row r of the transposed score tile (TMEM lane r)
-//   warp 4      control: one thread issues TMA (K,V once; Q_i,dO_i double-buffered) and all tcgen05.mma
+//   warps 0..7  compute: warp = (TMEM lane quarter, column half); a thread owns 64 columns of key row r of the
+//               transposed score tile — two warps per scheduler so one warp's TMEM/MUFU latency hides behind the other
+//   warp 8      control: one thread issues TMA (K,V once; Q_i,dO_i double-buffered) and all tcgen05.mma
 // Five GEMMs per (j, i) pair, all on the tensor core with TMEM accumulators (448 of 512 columns):
 //   S^T  = K Q_i^T        (cols   0..127)      dP^T = V dO_i^T       (cols 128..255)
 //   dV  += P^T dO_i       (cols 256..319)      dK  += dS^T Q_i       (cols 320..383)
@@ -19,7 +20,8 @@ namespace plm {
 
 constexpr int AB_T = 128;   // tile edge (keys per CTA, queries per step)
 constexpr int AB_HD = 64;
-constexpr int AB_THREADS = 160;
+constexpr int AB_CWARPS = 8;     // compute warps: (TMEM lane quarter) x (column half)
+constexpr int AB_THREADS = (AB_CWARPS + 1) * 32;
 constexpr int AB_TILE = AB_T * AB_HD * 2;  // 16 KB
 // K, V, (Q,dO) x2, P^T (2 blocks), dS^T (2 blocks), vectors (lse2, delta, seg) x2 stages, barriers
 constexpr int AB_VEC_BYTES = 2 * 3 * AB_T * 4;
@@ -64,7 +66,7 @@ attn_delta_kernel(const uint4* __restrict__ o, const uint4* __restrict__ dout, f
 // dq_acc fp32 [rows, d] -> inverse RoPE -> bf16 into dqkv[:, 0:d].  One thread per 8 columns.
 __global__ void __launch_bounds__(256)
 dq_finalize_kernel(const float* __restrict__ dq_acc, const float* __restrict__ table, __nv_bfloat16* __restrict__ dqkv,
-                   int64_t rows, int T, int d, int hd) {
+                   int64_t rows, int T, int d, int hd, float scale) {
   const int d8 = d >> 3;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= rows * d8) return;
@@ -72,7 +74,7 @@ dq_finalize_kernel(const float* __restrict__ dq_acc, const float* __restrict__ t
   const int c = static_cast<int>(idx - r * d8) * 8;
   const float4 a = __ldcs(reinterpret_cast<const float4*>(dq_acc + r * d + c));
   const float4 b = __ldcs(reinterpret_cast<const float4*>(dq_acc + r * d + c) + 1);
-  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  float v[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
   if (table) {
     const int pos = static_cast<int>(r % T);
     const int pair0 = (c % hd) >> 1;
@@ -93,6 +95,43 @@ dq_finalize_kernel(const float* __restrict__ dq_acc, const float* __restrict__ t
   o.z = pack_bf16x2(v[4], v[5]);
   o.w = pack_bf16x2(v[6], v[7]);
   *reinterpret_cast<uint4*>(dqkv + r * (3 * d) + c) = o;
+}
+
+// p = exp2(s * scale_log2 - lse2), optionally masked.  MASK: 0 = none (interior tile), 1 = causal/document/ragged.
+template <bool MASK>
+__device__ __forceinline__ void bwd_p_chunk(const uint32_t (&t)[32], float (&p)[32], const float* lse2, const int32_t* sg,
+                                            int kj, int qpos0, float scale_log2) {
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const float4 l = *reinterpret_cast<const float4*>(lse2 + q4 * 4);
+    const float lv[4] = {l.x, l.y, l.z, l.w};
+    int4 g = make_int4(0, 0, 0, 0);
+    if (MASK) g = *reinterpret_cast<const int4*>(sg + q4 * 4);
+    const int gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int q = q4 * 4 + e;
+      float v = ex2b(fmaf(__uint_as_float(t[q]), scale_log2, -lv[e]));
+      if (MASK) {
+        const int qi = qpos0 + q;
+        if (kj > qi || kj < gv[e]) v = 0.f;
+      }
+      p[q] = v;
+    }
+  }
+}
+
+__device__ __forceinline__ void store_bf16_row32(uint8_t* row_base, int r, int chunk0, const float (&v)[32]) {
+  // 32 consecutive K-columns of one A-operand row -> four 16-byte chunks of the 128B-swizzled row
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint4 o;
+    o.x = pack_bf16x2(v[8 * c + 0], v[8 * c + 1]);
+    o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+    o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+    o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    *reinterpret_cast<uint4*>(row_base + ((((chunk0 + c) & 7) ^ (r & 7)) << 4)) = o;
+  }
 }
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
@@ -151,12 +190,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
     mbar_init(s_full, 1);
     mbar_init(dp_full, 1);
-    mbar_init(pds_full, 4);
+    mbar_init(pds_full, AB_CWARPS);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 4);
+    mbar_init(dq_empty, AB_CWARPS);
     fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == AB_CWARPS) {
     tmem_alloc<512>(tmem_slot);
     tmem_relinquish();
   }
@@ -167,7 +206,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
                  tDQ = tmem_base + 384;
 
-  if (warp == 4) {
+  if (warp == AB_CWARPS) {
     if (lane == 0) {
       // ------------------------------------------------------------ control thread
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // K-major x K-major, N = 128 queries
@@ -235,28 +274,53 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------ compute warps
-    const int r = warp * 32 + lane;  // key row within the tile (S^T lane) / query row within the tile (dQ lane)
-    const int kj = j * AB_T + r;     // key position
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    // ------------------------------------------------------------ compute warps (8): warp = (lane quarter, column half)
+    const int quarter = warp & 3;
+    const int half = warp >> 2;              // query columns [64*half, 64*half+64) of S^T / dP^T; hd cols [32*half,+32) of dQ/dK/dV
+    const int r = quarter * 32 + lane;       // key row within the tile (S^T lane) / query row within the tile (dQ lane)
+    const int kj = j * AB_T + r;             // key position
+    const int ct = threadIdx.x;              // 0..255
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int64_t vec_base = (static_cast<int64_t>(b) * H + h) * T;
+
+    // per-query vectors of a step: threads 0..127 fetch lse & delta, threads 128..255 fetch seg_start
+    auto fetch = [&](int i, float& f0, float& f1, int32_t& g0) {
+      const int q = i * AB_T + (ct & 127);
+      const bool ok = q < T;
+      if (ct < 128) {
+        f0 = ok ? lse[vec_base + q] * 1.4426950408889634f : 0.f;
+        f1 = ok ? delta[vec_base + q] : 0.f;
+      } else {
+        g0 = ok ? (seg_start ? seg_start[seq0 + q] : 0) : 0x7fffffff;  // q >= T: nothing allowed
+      }
+    };
+    auto publish = [&](int st, float f0, float f1, int32_t g0) {
+      if (ct < 128) {
+        sLse[st * AB_T + ct] = f0;
+        sDelta[st * AB_T + ct] = f1;
+      } else {
+        sSeg[st * AB_T + ct - 128] = g0;
+      }
+    };
+    {
+      float f0 = 0.f, f1 = 0.f;
+      int32_t g0 = 0;
+      fetch(j, f0, f1, g0);
+      publish(0, f0, f1, g0);
+    }
 
     for (int it = 0; it < n_it; ++it) {
       const int i = j + it;
       const int st = it & 1;
-      // stage the per-query vectors of this step
-      {
-        const bool q_ok = i * AB_T + r < T;
-        const int64_t qrow = seq0 + i * AB_T + r;
-        const int64_t vidx = (static_cast<int64_t>(b) * H + h) * T + i * AB_T + r;
-        sLse[st * AB_T + r] = q_ok ? lse[vidx] * 1.4426950408889634f : 0.f;
-        sDelta[st * AB_T + r] = q_ok ? delta[vidx] : 0.f;
-        sSeg[st * AB_T + r] = q_ok ? (seg_start ? seg_start[qrow] : 0) : 0x7fffffff;  // q >= T: nothing allowed
-      }
-      named_bar_sync(1, 128);
-      const float* lse2 = sLse + st * AB_T;
-      const float* dl = sDelta + st * AB_T;
-      const int32_t* sg = sSeg + st * AB_T;
-      const int qbase = i * AB_T;
+      named_bar_sync(1, AB_CWARPS * 32);  // vectors of this step visible; everyone is done with the other buffer
+      float nf0 = 0.f, nf1 = 0.f;
+      int32_t ng0 = 0;
+      if (it + 1 < n_it) fetch(i + 1, nf0, nf1, ng0);  // prefetch: latency hidden behind this step's work
+      const float* lse2 = sLse + st * AB_T + half * 64;
+      const float* dl = sDelta + st * AB_T + half * 64;
+      const int32_t* sg = sSeg + st * AB_T + half * 64;
+      const int qpos0 = i * AB_T + half * 64;
+      const bool need_mask = (i == j) || (sSeg[st * AB_T + AB_T - 1] > j * AB_T);
 
       // previous step's dV/dK/dQ MMAs must have finished reading the P^T / dS^T buffers
       if (it > 0) {
@@ -264,154 +328,139 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tc_fence_after();
       }
 
-      // ---- P^T
+      // ---- P^T (64 columns per thread), kept in registers for dS^T
       mbar_wait(s_full, it & 1);
       tc_fence_after();
-      float p[AB_T];
+      float p[2][32];
+      uint8_t* prow = sP + half * AB_TILE + r * 128;
 #pragma unroll
-      for (int c = 0; c < AB_T / 32; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t t[32];
-        tmem_ld32(tS + lane_off + c * 32, t);
+        tmem_ld32(tS + lane_off + half * 64 + c * 32, t);
         tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const int qq = c * 32 + q;
-          const int qi = qbase + qq;
-          const bool ok = (kj <= qi) && (kj >= sg[qq]);
-          p[qq] = ok ? ex2b(__uint_as_float(t[q]) * scale_log2 - lse2[qq]) : 0.f;
-        }
+        if (need_mask)
+          bwd_p_chunk<true>(t, p[c], lse2 + c * 32, sg + c * 32, kj, qpos0 + c * 32, scale_log2);
+        else
+          bwd_p_chunk<false>(t, p[c], lse2 + c * 32, sg + c * 32, kj, qpos0 + c * 32, scale_log2);
+        store_bf16_row32(prow, r, c * 4, p[c]);
       }
-      uint8_t* prow = sP + r * 128;
-#pragma unroll
-      for (int c16 = 0; c16 < AB_T / 8; ++c16) {
-        uint4 v;
-        v.x = pack_bf16x2(p[c16 * 8 + 0], p[c16 * 8 + 1]);
-        v.y = pack_bf16x2(p[c16 * 8 + 2], p[c16 * 8 + 3]);
-        v.z = pack_bf16x2(p[c16 * 8 + 4], p[c16 * 8 + 5]);
-        v.w = pack_bf16x2(p[c16 * 8 + 6], p[c16 * 8 + 7]);
-        *reinterpret_cast<uint4*>(prow + (c16 >> 3) * AB_TILE + (((c16 & 7) ^ (r & 7)) << 4)) = v;
-      }
-      // ---- dS^T = P^T o (dP^T - delta) * scale
+      // ---- dS^T = P^T o (dP^T - delta)      (the softmax scale is applied once, in the dK / dQ epilogues)
       mbar_wait(dp_full, it & 1);
       tc_fence_after();
-      uint8_t* dsrow = sDS + r * 128;
+      uint8_t* dsrow = sDS + half * AB_TILE + r * 128;
 #pragma unroll
-      for (int c = 0; c < AB_T / 32; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t t[32];
-        tmem_ld32(tDP + lane_off + c * 32, t);
+        tmem_ld32(tDP + lane_off + half * 64 + c * 32, t);
         tmem_ld_wait();
+        float ds[32];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float ds[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int qq = c * 32 + g * 8 + e;
-            ds[e] = p[qq] * (__uint_as_float(t[g * 8 + e]) - dl[qq]) * scale;
-          }
-          uint4 v;
-          v.x = pack_bf16x2(ds[0], ds[1]);
-          v.y = pack_bf16x2(ds[2], ds[3]);
-          v.z = pack_bf16x2(ds[4], ds[5]);
-          v.w = pack_bf16x2(ds[6], ds[7]);
-          const int c16 = c * 4 + g;
-          *reinterpret_cast<uint4*>(dsrow + (c16 >> 3) * AB_TILE + (((c16 & 7) ^ (r & 7)) << 4)) = v;
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 dv = *reinterpret_cast<const float4*>(dl + c * 32 + q4 * 4);
+          ds[4 * q4 + 0] = p[c][4 * q4 + 0] * (__uint_as_float(t[4 * q4 + 0]) - dv.x);
+          ds[4 * q4 + 1] = p[c][4 * q4 + 1] * (__uint_as_float(t[4 * q4 + 1]) - dv.y);
+          ds[4 * q4 + 2] = p[c][4 * q4 + 2] * (__uint_as_float(t[4 * q4 + 2]) - dv.z);
+          ds[4 * q4 + 3] = p[c][4 * q4 + 3] * (__uint_as_float(t[4 * q4 + 3]) - dv.w);
         }
+        store_bf16_row32(dsrow, r, c * 4, ds);
       }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+
       if (it > 0) {
         // dQ of the previous step (overlaps this step's dV/dK MMAs): lane r now means QUERY row r of tile i-1
-        float* dst = dq_acc + (seq0 + (i - 1) * AB_T + r) * d + h * AB_HD;
+        float* dst = dq_acc + (seq0 + (i - 1) * AB_T + r) * d + h * AB_HD + half * 32;
         const bool dq_ok = (i - 1) * AB_T + r < T;
-#pragma unroll
-        for (int c = 0; c < AB_HD / 32; ++c) {
-          uint32_t t[32];
-          tmem_ld32(tDQ + lane_off + c * 32, t);
-          tmem_ld_wait();
-          if (!dq_ok) continue;
+        uint32_t t[32];
+        tmem_ld32(tDQ + lane_off + half * 32, t);
+        tmem_ld_wait();
+        if (dq_ok) {
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4)
-            red_add_f32x4(dst + c * 32 + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
+            red_add_f32x4(dst + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
                           __uint_as_float(t[4 * q4 + 2]), __uint_as_float(t[4 * q4 + 3]));
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_empty);
       }
+      if (it + 1 < n_it) publish(st ^ 1, nf0, nf1, ng0);
     }
 
-    // ---- tail: dQ of the last step, then dV / dK of this key tile
+    // ---- tail: dQ of the last step, then dV / dK of this key tile (32 head-dim columns per thread)
     mbar_wait(dq_full, (n_it - 1) & 1);
     tc_fence_after();
     {
-      float* dst = dq_acc + (seq0 + (j + n_it - 1) * AB_T + r) * d + h * AB_HD;
+      float* dst = dq_acc + (seq0 + (j + n_it - 1) * AB_T + r) * d + h * AB_HD + half * 32;
       const bool dq_ok = (j + n_it - 1) * AB_T + r < T;
-#pragma unroll
-      for (int c = 0; c < AB_HD / 32; ++c) {
-        uint32_t t[32];
-        tmem_ld32(tDQ + lane_off + c * 32, t);
-        tmem_ld_wait();
-        if (!dq_ok) continue;
+      uint32_t t[32];
+      tmem_ld32(tDQ + lane_off + half * 32, t);
+      tmem_ld_wait();
+      if (dq_ok) {
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4)
-          red_add_f32x4(dst + c * 32 + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
+          red_add_f32x4(dst + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
                         __uint_as_float(t[4 * q4 + 2]), __uint_as_float(t[4 * q4 + 3]));
       }
     }
-    __nv_bfloat16* dk_out = dqkv + (krow0 + r) * (3 * d) + d + h * AB_HD;
-    __nv_bfloat16* dv_out = dqkv + (krow0 + r) * (3 * d) + 2 * d + h * AB_HD;
-#pragma unroll
-    for (int c = 0; c < AB_HD / 32; ++c) {
+    const bool k_ok = kj < T;
+    {
       uint32_t t[32];
-      tmem_ld32(tDV + lane_off + c * 32, t);
+      tmem_ld32(tDV + lane_off + half * 32, t);
       tmem_ld_wait();
-      if (kj >= T) continue;
+      if (k_ok) {
+        __nv_bfloat16* dv_out = dqkv + (krow0 + r) * (3 * d) + 2 * d + h * AB_HD + half * 32;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 v;
-        v.x = pack_bf16x2(__uint_as_float(t[8 * g + 0]), __uint_as_float(t[8 * g + 1]));
-        v.y = pack_bf16x2(__uint_as_float(t[8 * g + 2]), __uint_as_float(t[8 * g + 3]));
-        v.z = pack_bf16x2(__uint_as_float(t[8 * g + 4]), __uint_as_float(t[8 * g + 5]));
-        v.w = pack_bf16x2(__uint_as_float(t[8 * g + 6]), __uint_as_float(t[8 * g + 7]));
-        *reinterpret_cast<uint4*>(dv_out + c * 32 + g * 8) = v;
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < AB_HD / 32; ++c) {
-      uint32_t t[32];
-      tmem_ld32(tDK + lane_off + c * 32, t);
-      tmem_ld_wait();
-      if (kj >= T) continue;
-      if (rope) {
-        const float4* tab = reinterpret_cast<const float4*>(rope + (static_cast<int64_t>(kj) * (AB_HD >> 1) + c * 16) * 2);
-#pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          const float4 cs = __ldg(tab + q4);
-          const float x0 = __uint_as_float(t[4 * q4 + 0]), x1 = __uint_as_float(t[4 * q4 + 1]);
-          const float y0 = __uint_as_float(t[4 * q4 + 2]), y1 = __uint_as_float(t[4 * q4 + 3]);
-          t[4 * q4 + 0] = __float_as_uint(x0 * cs.x + x1 * cs.y);
-          t[4 * q4 + 1] = __float_as_uint(x1 * cs.x - x0 * cs.y);
-          t[4 * q4 + 2] = __float_as_uint(y0 * cs.z + y1 * cs.w);
-          t[4 * q4 + 3] = __float_as_uint(y1 * cs.z - y0 * cs.w);
+        for (int g = 0; g < 4; ++g) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(t[8 * g + 0]), __uint_as_float(t[8 * g + 1]));
+          v.y = pack_bf16x2(__uint_as_float(t[8 * g + 2]), __uint_as_float(t[8 * g + 3]));
+          v.z = pack_bf16x2(__uint_as_float(t[8 * g + 4]), __uint_as_float(t[8 * g + 5]));
+          v.w = pack_bf16x2(__uint_as_float(t[8 * g + 6]), __uint_as_float(t[8 * g + 7]));
+          *reinterpret_cast<uint4*>(dv_out + g * 8) = v;
         }
       }
+    }
+    {
+      uint32_t t[32];
+      tmem_ld32(tDK + lane_off + half * 32, t);
+      tmem_ld_wait();
+      if (k_ok) {
+        float v[32];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 v;
-        v.x = pack_bf16x2(__uint_as_float(t[8 * g + 0]), __uint_as_float(t[8 * g + 1]));
-        v.y = pack_bf16x2(__uint_as_float(t[8 * g + 2]), __uint_as_float(t[8 * g + 3]));
-        v.z = pack_bf16x2(__uint_as_float(t[8 * g + 4]), __uint_as_float(t[8 * g + 5]));
-        v.w = pack_bf16x2(__uint_as_float(t[8 * g + 6]), __uint_as_float(t[8 * g + 7]));
-        *reinterpret_cast<uint4*>(dk_out + c * 32 + g * 8) = v;
+        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(t[e]) * scale;
+        if (rope) {  // rotate back: transpose of models/embeddings.py:15-30
+          const float4* tab =
+              reinterpret_cast<const float4*>(rope + (static_cast<int64_t>(kj) * (AB_HD >> 1) + half * 16) * 2);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 cs = __ldg(tab + q4);
+            const float x0 = v[4 * q4 + 0], x1 = v[4 * q4 + 1], y0 = v[4 * q4 + 2], y1 = v[4 * q4 + 3];
+            v[4 * q4 + 0] = x0 * cs.x + x1 * cs.y;
+            v[4 * q4 + 1] = x1 * cs.x - x0 * cs.y;
+            v[4 * q4 + 2] = y0 * cs.z + y1 * cs.w;
+            v[4 * q4 + 3] = y1 * cs.z - y0 * cs.w;
+          }
+        }
+        __nv_bfloat16* dk_out = dqkv + (krow0 + r) * (3 * d) + d + h * AB_HD + half * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
+          o.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+          o.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+          o.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+          *reinterpret_cast<uint4*>(dk_out + g * 8) = o;
+        }
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == AB_CWARPS) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -467,7 +516,7 @@ extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, 
   {
     const int64_t n = rows * (d / 8);
     dq_finalize_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-        dq_acc, rope_table, static_cast<__nv_bfloat16*>(dqkv), rows, T, d, hd);
+        dq_acc, rope_table, static_cast<__nv_bfloat16*>(dqkv), rows, T, d, hd, scale);
     rc = check_launch("dq_finalize");
   }
   return rc;

@@ -151,31 +151,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
       const int j = j_lo + it;
       mbar_wait(s_full, it & 1);
       tc_fence_after();
-      float x[ATT_BK];
+      // Two passes over the score tile in TMEM (reads are cheap): pass 1 = row max, pass 2 = exp2 / sum / P store.
+      // The row never sits in registers as a whole, and the softmax scale is folded into the exp2 argument.
+      const int kbase = j * ATT_BK;
+      const bool masked = (kbase + ATT_BK - 1 > qi) || (kbase < seg_lo);  // key kj allowed iff seg_lo <= kj <= qi
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < ATT_BK / 32; ++c) {
         uint32_t t[32];
         tmem_ld32(tS + lane_off + c * 32, t);
         tmem_ld_wait();
+        if (masked) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x[c * 32 + i] = __uint_as_float(t[i]) * scale_log2;
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);
-
-      // mask: key kj = j*128 + c allowed iff seg_lo <= kj <= qi
-      const int kbase = j * ATT_BK;
-      if (kbase + ATT_BK - 1 > qi || kbase < seg_lo) {
+          for (int i = 0; i < 32; ++i) {
+            const int kj = kbase + c * 32 + i;
+            if (kj > qi || kj < seg_lo) t[i] = 0xff800000u;  // -inf
+          }
+        }
 #pragma unroll
-        for (int c = 0; c < ATT_BK; ++c) {
-          const int kj = kbase + c;
-          if (kj > qi || kj < seg_lo) x[c] = -INFINITY;
+        for (int i = 0; i < 32; i += 4) {  // four independent chains: a single one is 128 dependent FMNMX
+          mx0 = fmaxf(mx0, __uint_as_float(t[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(t[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(t[i + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(t[i + 3]));
         }
       }
-      float mx = x[0];
-#pragma unroll
-      for (int c = 1; c < ATT_BK; ++c) mx = fmaxf(mx, x[c]);
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
 
       // previous P·V must be complete before P smem is overwritten or O is rescaled
       if (it > 0) {
@@ -202,24 +203,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
         }
       }
       const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
-      float psum = 0.f;
+      const float2 sc2 = make_float2(scale_log2, scale_log2);
+      const float2 nm2 = make_float2(-m_use, -m_use);
+      float2 ps0 = make_float2(0.f, 0.f), ps1 = make_float2(0.f, 0.f);
       uint8_t* prow = sP + r * 128;
 #pragma unroll
-      for (int c16 = 0; c16 < ATT_BK / 8; ++c16) {
-        float p[8];
+      for (int c = 0; c < ATT_BK / 32; ++c) {
+        uint32_t t[32];
+        tmem_ld32(tS + lane_off + c * 32, t);
+        tmem_ld_wait();
+        if (masked) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          p[i] = ex2(x[c16 * 8 + i] - m_use);
-          psum += p[i];
+          for (int i = 0; i < 32; ++i) {
+            const int kj = kbase + c * 32 + i;
+            if (kj > qi || kj < seg_lo) t[i] = 0xff800000u;
+          }
         }
-        uint4 v;
-        v.x = pack_bf16x2(p[0], p[1]);
-        v.y = pack_bf16x2(p[2], p[3]);
-        v.z = pack_bf16x2(p[4], p[5]);
-        v.w = pack_bf16x2(p[6], p[7]);
-        const int blk = c16 >> 3, cc = c16 & 7;
-        *reinterpret_cast<uint4*>(prow + blk * ATT_TILE_BYTES + ((cc ^ (r & 7)) << 4)) = v;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float2 e[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 a = __ffma2_rn(
+                make_float2(__uint_as_float(t[g * 8 + 2 * i]), __uint_as_float(t[g * 8 + 2 * i + 1])), sc2, nm2);
+            e[i] = make_float2(ex2(a.x), ex2(a.y));
+          }
+          ps0 = __fadd2_rn(ps0, __fadd2_rn(e[0], e[1]));
+          ps1 = __fadd2_rn(ps1, __fadd2_rn(e[2], e[3]));
+          uint4 v;
+          v.x = pack_bf16x2(e[0].x, e[0].y);
+          v.y = pack_bf16x2(e[1].x, e[1].y);
+          v.z = pack_bf16x2(e[2].x, e[2].y);
+          v.w = pack_bf16x2(e[3].x, e[3].y);
+          const int c16 = c * 4 + g;
+          *reinterpret_cast<uint4*>(prow + (c16 >> 3) * ATT_TILE_BYTES + (((c16 & 7) ^ (r & 7)) << 4)) = v;
+        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);  // S may be overwritten by the next Q K^T
+      const float psum = (ps0.x + ps0.y) + (ps1.x + ps1.y);
       l_run += psum;
       fence_proxy_async_smem();
       tc_fence_before();

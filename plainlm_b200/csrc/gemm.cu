@@ -30,6 +30,7 @@ struct GemmParams {
   int splits;
   int rope_cols, rope_T, head_dim;
   int num_m, num_n, kblocks;
+  int n_fastest;  // tile rasterisation: 0 = consecutive tiles walk M (B tile reused), 1 = walk N (A tile reused)
 };
 
 template <int BN>
@@ -47,8 +48,13 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_b
   const int tiles = p.num_m * p.num_n;
   const int tile = w % tiles;
   const int split = w / tiles;
-  m_blk = tile % p.num_m;
-  n_blk = tile / p.num_m;
+  if (p.n_fastest) {
+    n_blk = tile % p.num_n;
+    m_blk = tile / p.num_n;
+  } else {
+    m_blk = tile % p.num_m;
+    n_blk = tile / p.num_m;
+  }
   const int per = (p.kblocks + p.splits - 1) / p.splits;
   kb0 = split * per;
   kb1 = min(p.kblocks, kb0 + per);
@@ -331,17 +337,22 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   p.kblocks = static_cast<int>((a->K + BK - 1) / BK);
   p.num_m = static_cast<int>((a->M + BM - 1) / BM);
 
-  // Tile width: fewer, wider tiles feed the tensor core best (one 128x256x16 MMA reads 12 KB of smem per 128 cycles);
-  // fall back to BN=128 when 256-wide tiles leave a badly quantised last wave.
+  // Tile width: 128x256 tiles feed the tensor core best (one 128x256x16 MMA reads 12 KB of smem per 128 cycles;
+  // a 128x128x16 MMA reads 8 KB per 64 cycles, which is the smem bandwidth limit).  BN=128 only for narrow N.
   const int sms = sm_count();
-  int bn = 256;
+  int bn = a->N <= 128 ? 128 : 256;
   {
-    const int64_t t256 = p.num_m * ((a->N + 255) / 256), t128 = p.num_m * ((a->N + 127) / 128);
-    const double c256 = static_cast<double>((t256 + sms - 1) / sms) * 1.0;
-    const double c128 = static_cast<double>((t128 + sms - 1) / sms) * 0.55;
-    if (a->N <= 128 || c128 < c256) bn = 128;
     const int forced = env_int("PLM_GEMM_BN", 0);
     if (forced == 128 || forced == 256) bn = forced;
+  }
+  // Rasterisation: the ~148 tiles in flight should share the operand that does NOT fit in L2.  Walking M keeps one
+  // B tile hot and streams A once per N-block (fine when A fits in L2); walking N reads each A row-block once.
+  {
+    const double a_bytes = 2.0 * static_cast<double>(a->M) * static_cast<double>(a->K);
+    const double b_bytes = 2.0 * static_cast<double>(a->N) * static_cast<double>(a->K);
+    p.n_fastest = (a_bytes > 48e6 && b_bytes < a_bytes) ? 1 : 0;
+    const int forced = env_int("PLM_GEMM_RASTER", -1);
+    if (forced == 0 || forced == 1) p.n_fastest = forced;
   }
   p.num_n = static_cast<int>((a->N + bn - 1) / bn);
 

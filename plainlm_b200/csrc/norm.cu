@@ -49,7 +49,7 @@ rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __n
 }
 
 template <int VPL>
-__global__ void __launch_bounds__(NORM_WARPS * 32)
+__global__ void __launch_bounds__(NORM_WARPS * 32, (VPL <= 8) ? 2 : 1)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                    const float* __restrict__ rstd, const float* dx_in, float* dx_out,
                    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dw_partial, int64_t rows) {
@@ -58,41 +58,45 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const float4* wr = reinterpret_cast<const float4*>(w);
-  float4 ww[VPL], dw[VPL];
+  float4 dw[VPL];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    ww[i] = __ldg(wr + i * 32 + lane);
-    dw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int i = 0; i < VPL; ++i) dw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * NORM_WARPS + warp; row < rows;
        row += static_cast<int64_t>(gridDim.x) * NORM_WARPS) {
     const float4* xr = reinterpret_cast<const float4*>(x + row * D);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + row * D);
     const float r = rstd[row];
-    float4 xh[VPL], g[VPL];
+    // only the raw row (x fp32, dy bf16) stays in registers; w is re-read from L1 (keeps 2 blocks resident per SM)
+    float4 xv[VPL];
+    uint2 dv[VPL];
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      const float4 xv = __ldcs(xr + i * 32 + lane);
-      const uint2 dv = __ldcs(dyr + i * 32 + lane);
-      const float d0 = bf16_lo(dv.x), d1 = bf16_hi(dv.x), d2 = bf16_lo(dv.y), d3 = bf16_hi(dv.y);
-      xh[i] = make_float4(xv.x * r, xv.y * r, xv.z * r, xv.w * r);
-      g[i] = make_float4(d0 * ww[i].x, d1 * ww[i].y, d2 * ww[i].z, d3 * ww[i].w);
-      dot += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
-      dw[i].x += d0 * xh[i].x;
-      dw[i].y += d1 * xh[i].y;
-      dw[i].z += d2 * xh[i].z;
-      dw[i].w += d3 * xh[i].w;
+      xv[i] = __ldcs(xr + i * 32 + lane);
+      dv[i] = __ldcs(dyr + i * 32 + lane);
     }
-    dot = warp_sum(dot) * (1.0f / D);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float4 ww = __ldg(wr + i * 32 + lane);
+      dot += bf16_lo(dv[i].x) * ww.x * xv[i].x + bf16_hi(dv[i].x) * ww.y * xv[i].y +
+             bf16_lo(dv[i].y) * ww.z * xv[i].z + bf16_hi(dv[i].y) * ww.w * xv[i].w;
+    }
+    dot = warp_sum(dot) * r * (1.0f / D);  // mean_j (dy_j w_j xhat_j)
     float4* dxo = reinterpret_cast<float4*>(dx_out + row * D);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
+      const float4 ww = __ldg(wr + i * 32 + lane);
+      const float d0 = bf16_lo(dv[i].x), d1 = bf16_hi(dv[i].x), d2 = bf16_lo(dv[i].y), d3 = bf16_hi(dv[i].y);
+      const float h0 = xv[i].x * r, h1 = xv[i].y * r, h2 = xv[i].z * r, h3 = xv[i].w * r;
+      dw[i].x += d0 * h0;
+      dw[i].y += d1 * h1;
+      dw[i].z += d2 * h2;
+      dw[i].w += d3 * h3;
       float4 o;
-      o.x = r * (g[i].x - xh[i].x * dot);
-      o.y = r * (g[i].y - xh[i].y * dot);
-      o.z = r * (g[i].z - xh[i].z * dot);
-      o.w = r * (g[i].w - xh[i].w * dot);
+      o.x = r * (d0 * ww.x - h0 * dot);
+      o.y = r * (d1 * ww.y - h1 * dot);
+      o.z = r * (d2 * ww.z - h2 * dot);
+      o.w = r * (d3 * ww.w - h3 * dot);
       if (dx_in) {
         const float4 a = __ldcs(reinterpret_cast<const float4*>(dx_in + row * D) + i * 32 + lane);
         o.x += a.x;

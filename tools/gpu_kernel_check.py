@@ -349,66 +349,61 @@ def case_bandwidth():
   return res
 
 
+def _time(fn, iters=10):
+  import torch
+
+  for _ in range(3):
+    fn()
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(iters):
+    fn()
+  e1.record()
+  torch.cuda.synchronize()
+  return e0.elapsed_time(e1) / iters
+
+
 def case_gemm_perf():
-  """Timing of the 420M GEMM shapes against torch.matmul (cuBLASLt)."""
+  """Every GEMM of the 420M micro-step (fwd / dgrad / wgrad), swept over tile width and rasterisation, vs cuBLASLt."""
   import torch
   from plainlm_b200 import ops, _lib
 
   dev = 'cuda'
   out = []
   M = 16384
-  shapes = [('qkv', M, 3072, 1024), ('out', M, 1024, 1024), ('fc1', M, 5632, 1024), ('fc2', M, 1024, 2816),
-            ('lm_head', M, 50280, 1024)]
-  for name, m, n, k in shapes:
-    a = torch.randn(m, k, device=dev).to(torch.bfloat16)
-    b = torch.randn(n, k, device=dev).to(torch.bfloat16)
-    c = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
-
-    def run_ours():
-      ops.gemm(a, b, c)
-
-    def run_torch():
-      torch.matmul(a, b.t(), out=c)
-
-    rec = {'case': f'gemm_perf {name} {m}x{n}x{k}'}
-    for label, fn in (('ours', run_ours), ('cublas', run_torch)):
-      for _ in range(3):
-        fn()
-      torch.cuda.synchronize()
-      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-      e0.record()
-      iters = 10
-      for _ in range(iters):
-        fn()
-      e1.record()
-      torch.cuda.synchronize()
-      ms = e0.elapsed_time(e1) / iters
-      rec[label + '_ms'] = ms
-      rec[label + '_tflops'] = 2.0 * m * n * k / ms / 1e9
-    out.append(rec)
-  # wgrad / dgrad variants on the fc1 shape
-  m, n, k = M, 5632, 1024
-  dy = torch.randn(m, n, device=dev).to(torch.bfloat16)
-  x = torch.randn(m, k, device=dev).to(torch.bfloat16)
-  w = torch.randn(n, k, device=dev).to(torch.bfloat16)
-  dw = torch.zeros(n, k, device=dev)
-  dx = torch.empty(m, k, device=dev, dtype=torch.bfloat16)
-  for label, fn, flops in (
-    ('wgrad fc1', lambda: ops.gemm(dy, x, dw, a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ATOMIC_F32, splits=0),
-     2.0 * m * n * k),
-    ('dgrad fc1', lambda: ops.gemm(dy, w, dx, a_kmajor=True, b_kmajor=False), 2.0 * m * n * k),
-  ):
-    for _ in range(3):
-      fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-      fn()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    out.append({'case': f'gemm_perf {label}', 'ours_ms': ms, 'ours_tflops': flops / ms / 1e9})
+  layers = [('qkv', 3072, 1024), ('out', 1024, 1024), ('fc1', 5632, 1024), ('fc2', 1024, 2816), ('lm_head', 50280, 1024)]
+  for name, n, k in layers:
+    x = torch.randn(M, k, device=dev).to(torch.bfloat16)
+    w = torch.randn(n, k, device=dev).to(torch.bfloat16)
+    y = torch.empty(M, n, device=dev, dtype=torch.bfloat16)
+    dy = torch.randn(M, n, device=dev).to(torch.bfloat16)
+    dx = torch.empty(M, k, device=dev, dtype=torch.bfloat16)
+    dw = torch.zeros(n, k, device=dev)
+    flops = 2.0 * M * n * k
+    variants = {
+      'fwd': lambda: ops.gemm(x, w, y),
+      'dgrad': lambda: ops.gemm(dy, w, dx, a_kmajor=True, b_kmajor=False),
+      'wgrad': lambda: ops.gemm(dy, x, dw, a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ATOMIC_F32, splits=0),
+    }
+    cublas = {
+      'fwd': lambda: torch.matmul(x, w.t(), out=y),
+      'dgrad': lambda: torch.matmul(dy, w, out=dx),
+      'wgrad': lambda: torch.matmul(dy.t(), x),
+    }
+    for vname, fn in variants.items():
+      rec = {'case': f'{name} {vname} M{M} N{n} K{k}'}
+      for bn in (256, 128):
+        for raster in (0, 1):
+          os.environ['PLM_GEMM_BN'] = str(bn)
+          os.environ['PLM_GEMM_RASTER'] = str(raster)
+          rec[f'bn{bn}_r{raster}'] = round(flops / _time(fn, 6) / 1e9, 0)
+      os.environ.pop('PLM_GEMM_BN')
+      os.environ.pop('PLM_GEMM_RASTER')
+      rec['auto'] = round(flops / _time(fn, 6) / 1e9, 0)
+      rec['cublas'] = round(flops / _time(cublas[vname], 6) / 1e9, 0)
+      out.append(rec)
+    del x, w, y, dy, dx, dw
   return out
 
 
