@@ -361,11 +361,21 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
     PLM_REQUIRE(splits <= 1, "gemm: split-K needs the atomic epilogue");
     splits = 1;
   } else if (splits <= 0) {
+    // Pick the split count that fills whole waves of the persistent grid: efficiency = items / (waves * SMs), with a
+    // small penalty per split (each split adds one fp32 red.add pass over the output tile).
     const int tiles = p.num_m * p.num_n;
+    const int max_splits = p.kblocks / 8 > 0 ? (p.kblocks / 8 < 32 ? p.kblocks / 8 : 32) : 1;  // >= 8 k-blocks each
+    double best = -1.0;
     splits = 1;
-    if (tiles < sms) splits = (sms + tiles - 1) / tiles;
-    const int max_splits = p.kblocks / 8 > 0 ? p.kblocks / 8 : 1;  // keep >= 8 k-blocks per split
-    if (splits > max_splits) splits = max_splits;
+    for (int s = 1; s <= max_splits; ++s) {
+      const int items = tiles * s;
+      const int waves = (items + sms - 1) / sms;
+      const double eff = static_cast<double>(items) / (static_cast<double>(waves) * sms) - 0.004 * (s - 1);
+      if (eff > best + 1e-9) {
+        best = eff;
+        splits = s;
+      }
+    }
   }
   if (splits > p.kblocks) splits = p.kblocks;
   {
