@@ -1,16 +1,18 @@
 // Flash-attention backward on tcgen05 (backward of models/transformer.py:53-63, reached from engine/engine.py:120).
 //
-// One CTA per (128-key tile j, head, batch), looping over the query tiles i >= j that can see it. 160 threads:
+// One CTA per (128-key tile j, head, batch), looping over the query tiles i >= j that can see it. 320 threads:
 //   warps 0..7  compute: warp = (TMEM lane quarter, column half); a thread owns 64 columns of key row r of the
 //               transposed score tile — two warps per scheduler so one warp's TMEM/MUFU latency hides behind the other
-//   warp 8      control: one thread issues TMA (K,V once; Q_i,dO_i double-buffered) and all tcgen05.mma
-// Five GEMMs per (j, i) pair, all on the tensor core with TMEM accumulators (448 of 512 columns):
+//   warp 8      MMA issuer (one thread, all tcgen05.mma)      warp 9  TMA producer (K,V once; Q_i,dO_i 3-stage ring)
+// Five GEMMs per (j, i) pair, all on the tensor core, all 512 TMEM columns in use:
 //   S^T  = K Q_i^T        (cols   0..127)      dP^T = V dO_i^T       (cols 128..255)
 //   dV  += P^T dO_i       (cols 256..319)      dK  += dS^T Q_i       (cols 320..383)
 //   dQ_i = dS K           (cols 384..447) -> fp32 red.add into dq_acc (finalised by dq_finalize_kernel)
-// P^T and dS^T are written once to swizzled smem as K-major A operands; the SAME dS^T buffer is re-read as an
-// MN-major A operand for the dQ GEMM, and Q_i / dO_i / K are consumed as MN-major B operands straight from their TMA
-// boxes — no transposes anywhere.  dK and dQ are rotated back through RoPE in the epilogues.
+//   P^T as packed bf16    (cols 448..511) -> A operand of the dV GEMM read straight from tensor memory
+// dS^T is written once to swizzled smem as a K-major A operand (dK) and re-read MN-major for the dQ GEMM; Q_i / dO_i /
+// K are consumed as MN-major B operands straight from their TMA boxes — no transposes anywhere.  The issue order
+// (dV_i, S_{i+1} | dK_i, dQ_i, dP_{i+1}) keeps the tensor pipe busy while the compute warps do the exp / dS math of
+// the neighbouring step.  dK and dQ are rotated back through RoPE in the epilogues.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -21,11 +23,12 @@ namespace plm {
 constexpr int AB_T = 128;   // tile edge (keys per CTA, queries per step)
 constexpr int AB_HD = 64;
 constexpr int AB_CWARPS = 8;     // compute warps: (TMEM lane quarter) x (column half)
-constexpr int AB_THREADS = (AB_CWARPS + 1) * 32;
+constexpr int AB_THREADS = (AB_CWARPS + 2) * 32;  // + MMA issuer warp + TMA producer warp
+constexpr int AB_STAGES = 3;       // Q_i / dO_i ring
 constexpr int AB_TILE = AB_T * AB_HD * 2;  // 16 KB
-// K, V, (Q,dO) x2, P^T (2 blocks), dS^T (2 blocks), vectors (lse2, delta, seg) x2 stages, barriers
+// K, V, (Q,dO) x AB_STAGES, dS^T (2 blocks), vectors (lse2, delta, seg) x2 stages, barriers
 constexpr int AB_VEC_BYTES = 2 * 3 * AB_T * 4;
-constexpr int AB_SMEM = AB_TILE * (2 + 4 + 2 + 2) + AB_VEC_BYTES + 128;
+constexpr int AB_SMEM = AB_TILE * (2 + 2 * AB_STAGES + 2) + AB_VEC_BYTES + 256;
 
 __device__ __forceinline__ float ex2b(float x) {
   float y;
@@ -142,23 +145,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = smem + AB_TILE;
-  uint8_t* sQ = smem + 2 * AB_TILE;    // [2]
-  uint8_t* sDO = smem + 4 * AB_TILE;   // [2]
-  uint8_t* sP = smem + 6 * AB_TILE;    // P^T : 2 blocks (q 0..63 | 64..127), each [128 kv rows x 128 B]
-  uint8_t* sDS = smem + 8 * AB_TILE;   // dS^T: same layout
-  float* sLse = reinterpret_cast<float*>(smem + 10 * AB_TILE);  // [2][128]  lse * log2(e)
-  float* sDelta = sLse + 2 * AB_T;                               // [2][128]
-  int32_t* sSeg = reinterpret_cast<int32_t*>(sDelta + 2 * AB_T); // [2][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 10 * AB_TILE + AB_VEC_BYTES);
+  uint8_t* sQ = smem + 2 * AB_TILE;                    // [AB_STAGES]
+  uint8_t* sDO = smem + (2 + AB_STAGES) * AB_TILE;     // [AB_STAGES]
+  uint8_t* sDS = smem + (2 + 2 * AB_STAGES) * AB_TILE; // dS^T: 2 blocks (q 0..63 | 64..127), each [128 kv rows x 128 B]
+  float* sLse = reinterpret_cast<float*>(smem + (4 + 2 * AB_STAGES) * AB_TILE);  // [2][128]  lse * log2(e)
+  float* sDelta = sLse + 2 * AB_T;                                                 // [2][128]
+  int32_t* sSeg = reinterpret_cast<int32_t*>(sDelta + 2 * AB_T);                   // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (4 + 2 * AB_STAGES) * AB_TILE + AB_VEC_BYTES);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;   // [2]
-  uint64_t* qdo_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* dp_full = bars + 6;
-  uint64_t* pds_full = bars + 7;
-  uint64_t* dq_full = bars + 8;
-  uint64_t* dq_empty = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* qdo_full = bars + 1;                // [AB_STAGES]
+  uint64_t* qdo_empty = bars + 1 + AB_STAGES;   // [AB_STAGES]
+  uint64_t* s_full = bars + 1 + 2 * AB_STAGES;
+  uint64_t* dp_full = s_full + 1;
+  uint64_t* p_ready = s_full + 2;
+  uint64_t* ds_ready = s_full + 3;
+  uint64_t* dq_full = s_full + 4;
+  uint64_t* dq_empty = s_full + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
 
   if ((smem_u32(smem) & 1023u) != 0) return;
 
@@ -184,13 +187,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < AB_STAGES; ++s) {
       mbar_init(&qdo_full[s], 1);
       mbar_init(&qdo_empty[s], 1);
     }
     mbar_init(s_full, 1);
     mbar_init(dp_full, 1);
-    mbar_init(pds_full, AB_CWARPS);
+    mbar_init(p_ready, AB_CWARPS);
+    mbar_init(ds_ready, AB_CWARPS);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, AB_CWARPS);
     fence_barrier_init();
@@ -203,74 +207,87 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: S^T 0..127 | dP^T 128..255 | dV 256..319 | dK 320..383 | dQ 384..447 | P^T (bf16 pairs) 448..511
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
-                 tDQ = tmem_base + 384;
+                 tDQ = tmem_base + 384, tP = tmem_base + 448;
 
-  if (warp == AB_CWARPS) {
+  if (warp == AB_CWARPS + 1) {
+    // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      // ------------------------------------------------------------ control thread
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // K-major x K-major, N = 128 queries
-      constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);   // A K-major, B MN-major, N = 64 (dV, dK)
-      constexpr uint32_t idesc_nn = make_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major (dQ)
       mbar_arrive_expect_tx(kv_full, 2 * AB_TILE);
       tma_load_2d(sK, &tmQKV, kv_full, d + h * AB_HD, static_cast<int>(krow0));
       tma_load_2d(sV, &tmQKV, kv_full, 2 * d + h * AB_HD, static_cast<int>(krow0));
-      {
-        const int qr = static_cast<int>(seq0 + j * AB_T);
-        mbar_arrive_expect_tx(&qdo_full[0], 2 * AB_TILE);
-        tma_load_2d(sQ, &tmQKV, &qdo_full[0], h * AB_HD, qr);
-        tma_load_2d(sDO, &tmDO, &qdo_full[0], h * AB_HD, qr);
-      }
-      mbar_wait(kv_full, 0);
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
       for (int it = 0; it < n_it; ++it) {
-        const int st = it & 1;
-        const uint32_t q_addr = smem_u32(sQ + st * AB_TILE), do_addr = smem_u32(sDO + st * AB_TILE);
-        mbar_wait(&qdo_full[st], (it >> 1) & 1);
+        const int st = it % AB_STAGES, use = it / AB_STAGES;
+        mbar_wait(&qdo_empty[st], (use & 1) ^ 1);
+        const int qr = static_cast<int>(seq0 + (j + it) * AB_T);
+        mbar_arrive_expect_tx(&qdo_full[st], 2 * AB_TILE);
+        tma_load_2d(sQ + st * AB_TILE, &tmQKV, &qdo_full[st], h * AB_HD, qr);
+        tma_load_2d(sDO + st * AB_TILE, &tmDO, &qdo_full[st], h * AB_HD, qr);
+      }
+    }
+  } else if (warp == AB_CWARPS) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer.  Tensor-pipe order per step `it`:
+      //   dV_it (needs P^T_it) , S^T_{it+1} | dK_it , dQ_it (need dS^T_it) , dP^T_{it+1}
+      // so the exp-heavy half of step it+1 overlaps the dK/dQ/dP MMAs of step it, and its dS half overlaps dV/S.
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // K-major x K-major, N = 128 queries
+      constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);   // A K-major (smem or TMEM), B MN-major, N = 64
+      constexpr uint32_t idesc_nn = make_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major (dQ)
+      mbar_wait(kv_full, 0);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), ds_addr = smem_u32(sDS);
+      auto issue_s = [&](int it) {
+        const int st = it % AB_STAGES;
+        mbar_wait(&qdo_full[st], (it / AB_STAGES) & 1);
         tc_fence_after();
-        // S^T = K Q^T ; dP^T = V dO^T      (TMEM regions are free: pds_full(it-1) was awaited below)
+        const uint32_t q_addr = smem_u32(sQ + st * AB_TILE);
 #pragma unroll
         for (int k = 0; k < AB_HD / 16; ++k)
           umma_ss(tS, make_smem_desc_sw128(k_addr + k * 32, 16, 1024), make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
                   idesc_s, k > 0 ? 1u : 0u);
         umma_commit(s_full);
+      };
+      auto issue_dp = [&](int it) {
+        const int st = it % AB_STAGES;
+        const uint32_t do_addr = smem_u32(sDO + st * AB_TILE);
 #pragma unroll
         for (int k = 0; k < AB_HD / 16; ++k)
           umma_ss(tDP, make_smem_desc_sw128(v_addr + k * 32, 16, 1024),
                   make_smem_desc_sw128(do_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
         umma_commit(dp_full);
-        // prefetch next Q / dO
-        if (it + 1 < n_it) {
-          const int nst = (it + 1) & 1;
-          mbar_wait(&qdo_empty[nst], (((it + 1) >> 1) & 1) ^ 1);
-          const int qr = static_cast<int>(seq0 + (j + it + 1) * AB_T);
-          mbar_arrive_expect_tx(&qdo_full[nst], 2 * AB_TILE);
-          tma_load_2d(sQ + nst * AB_TILE, &tmQKV, &qdo_full[nst], h * AB_HD, qr);
-          tma_load_2d(sDO + nst * AB_TILE, &tmDO, &qdo_full[nst], h * AB_HD, qr);
-        }
-        mbar_wait(pds_full, it & 1);
+      };
+      issue_s(0);
+      issue_dp(0);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it % AB_STAGES;
+        const uint32_t q_addr = smem_u32(sQ + st * AB_TILE), do_addr = smem_u32(sDO + st * AB_TILE);
+        // ---- dV += P^T dO   (A = P^T from tensor memory: 8 columns per 16-query K-step)
+        mbar_wait(p_ready, it & 1);
         tc_fence_after();
-        // dV += P^T dO ; dK += dS^T Q      (reduction over the 128 queries of this step)
 #pragma unroll
         for (int k = 0; k < AB_T / 16; ++k)
-          umma_ss(tDV, make_smem_desc_sw128(p_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 16, 1024),
-                  make_smem_desc_sw128(do_addr + k * 2048, AB_TILE, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
+          umma_ts(tDV, tP + k * 8, make_smem_desc_sw128(do_addr + k * 2048, AB_TILE, 1024), idesc_kn,
+                  (it > 0 || k > 0) ? 1u : 0u);
+        if (it + 1 < n_it) issue_s(it + 1);  // S^T region is free: every compute warp read it before p_ready
+        // ---- dK += dS^T Q ; dQ = dS K
+        mbar_wait(ds_ready, it & 1);
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < AB_T / 16; ++k)
           umma_ss(tDK, make_smem_desc_sw128(ds_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 16, 1024),
                   make_smem_desc_sw128(q_addr + k * 2048, AB_TILE, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
-        // dQ = dS K : A = dS^T buffer read MN-major (M = queries, 64 per block, blocks AB_TILE apart), B = K MN-major
         if (it > 0) {
           mbar_wait(dq_empty, (it - 1) & 1);
           tc_fence_after();
         }
+        // A = dS^T buffer read MN-major (M = queries, 64 per block, blocks AB_TILE apart), B = K MN-major
 #pragma unroll
         for (int k = 0; k < AB_T / 16; ++k)
           umma_ss(tDQ, make_smem_desc_sw128(ds_addr + k * 2048, AB_TILE, 1024),
                   make_smem_desc_sw128(k_addr + k * 2048, AB_TILE, 1024), idesc_nn, k > 0 ? 1u : 0u);
         umma_commit(&qdo_empty[st]);
         umma_commit(dq_full);
+        if (it + 1 < n_it) issue_dp(it + 1);  // dP^T region is free: every compute warp read it before ds_ready
       }
     }
   } else {
@@ -302,6 +319,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         sSeg[st * AB_T + ct - 128] = g0;
       }
     };
+    auto dq_flush = [&](int i_tile) {  // dQ of query tile i_tile: lane r now means QUERY row r; 32 head-dim cols/thread
+      float* dst = dq_acc + (seq0 + i_tile * AB_T + r) * d + h * AB_HD + half * 32;
+      const bool dq_ok = i_tile * AB_T + r < T;
+      uint32_t t[32];
+      tmem_ld32(tDQ + lane_off + half * 32, t);
+      tmem_ld_wait();
+      if (dq_ok) {
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4)
+          red_add_f32x4(dst + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
+                        __uint_as_float(t[4 * q4 + 2]), __uint_as_float(t[4 * q4 + 3]));
+      }
+    };
     {
       float f0 = 0.f, f1 = 0.f;
       int32_t g0 = 0;
@@ -322,17 +352,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const int qpos0 = i * AB_T + half * 64;
       const bool need_mask = (i == j) || (sSeg[st * AB_T + AB_T - 1] > j * AB_T);
 
-      // previous step's dV/dK/dQ MMAs must have finished reading the P^T / dS^T buffers
-      if (it > 0) {
-        mbar_wait(dq_full, (it - 1) & 1);
-        tc_fence_after();
-      }
-
-      // ---- P^T (64 columns per thread), kept in registers for dS^T
+      // ---- P^T (64 query columns per thread): registers for dS^T, packed bf16 pairs into tensor memory for dV
       mbar_wait(s_full, it & 1);
       tc_fence_after();
       float p[2][32];
-      uint8_t* prow = sP + half * AB_TILE + r * 128;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t t[32];
@@ -342,8 +365,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
           bwd_p_chunk<true>(t, p[c], lse2 + c * 32, sg + c * 32, kj, qpos0 + c * 32, scale_log2);
         else
           bwd_p_chunk<false>(t, p[c], lse2 + c * 32, sg + c * 32, kj, qpos0 + c * 32, scale_log2);
-        store_bf16_row32(prow, r, c * 4, p[c]);
       }
+      {
+        uint32_t w[32];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          w[e] = pack_bf16x2(p[0][2 * e], p[0][2 * e + 1]);
+          w[16 + e] = pack_bf16x2(p[1][2 * e], p[1][2 * e + 1]);
+        }
+        tmem_st32(tP + lane_off + half * 32, w);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+
+      // ---- dQ of the previous step; its completion also means dK/dQ MMAs no longer read the dS^T buffer
+      if (it > 0) {
+        mbar_wait(dq_full, (it - 1) & 1);
+        tc_fence_after();
+        dq_flush(i - 1);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_empty);
+      }
+
       // ---- dS^T = P^T o (dP^T - delta)      (the softmax scale is applied once, in the dK / dQ epilogues)
       mbar_wait(dp_full, it & 1);
       tc_fence_after();
@@ -367,44 +413,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
-
-      if (it > 0) {
-        // dQ of the previous step (overlaps this step's dV/dK MMAs): lane r now means QUERY row r of tile i-1
-        float* dst = dq_acc + (seq0 + (i - 1) * AB_T + r) * d + h * AB_HD + half * 32;
-        const bool dq_ok = (i - 1) * AB_T + r < T;
-        uint32_t t[32];
-        tmem_ld32(tDQ + lane_off + half * 32, t);
-        tmem_ld_wait();
-        if (dq_ok) {
-#pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4)
-            red_add_f32x4(dst + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
-                          __uint_as_float(t[4 * q4 + 2]), __uint_as_float(t[4 * q4 + 3]));
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dq_empty);
-      }
+      if (lane == 0) mbar_arrive(ds_ready);
       if (it + 1 < n_it) publish(st ^ 1, nf0, nf1, ng0);
     }
 
     // ---- tail: dQ of the last step, then dV / dK of this key tile (32 head-dim columns per thread)
     mbar_wait(dq_full, (n_it - 1) & 1);
     tc_fence_after();
-    {
-      float* dst = dq_acc + (seq0 + (j + n_it - 1) * AB_T + r) * d + h * AB_HD + half * 32;
-      const bool dq_ok = (j + n_it - 1) * AB_T + r < T;
-      uint32_t t[32];
-      tmem_ld32(tDQ + lane_off + half * 32, t);
-      tmem_ld_wait();
-      if (dq_ok) {
-#pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4)
-          red_add_f32x4(dst + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
-                        __uint_as_float(t[4 * q4 + 2]), __uint_as_float(t[4 * q4 + 3]));
-      }
-    }
+    dq_flush(j + n_it - 1);
     const bool k_ok = kj < T;
     {
       uint32_t t[32];
