@@ -1,9 +1,9 @@
 // Flash-attention backward on tcgen05 (backward of models/transformer.py:53-63, reached from engine/engine.py:120).
 //
-// One CTA per (128-key tile j, head, batch), looping over the query tiles i >= j that can see it. 320 threads:
-//   warps 0..7  compute: warp = (TMEM lane quarter, column half); a thread owns 64 columns of key row r of the
-//               transposed score tile — two warps per scheduler so one warp's TMEM/MUFU latency hides behind the other
-//   warp 8      MMA issuer (one thread, all tcgen05.mma)      warp 9  TMA producer (K,V once; Q_i,dO_i 3-stage ring)
+// One CTA per (128-key tile j, head, batch), looping over the query tiles i >= j that can see it. 576 threads:
+//   warps 0..15 compute: warp = (TMEM lane quarter, column quarter); a thread owns 32 columns of key row r of the
+//               transposed score tile — four warps per scheduler so TMEM / smem / MUFU latencies overlap
+//   warp 16     MMA issuer (one thread, all tcgen05.mma)      warp 17 TMA producer (K,V once; Q_i,dO_i 3-stage ring)
 // Five GEMMs per (j, i) pair, all on the tensor core, all 512 TMEM columns in use:
 //   S^T  = K Q_i^T        (cols   0..127)      dP^T = V dO_i^T       (cols 128..255)
 //   dV  += P^T dO_i       (cols 256..319)      dK  += dS^T Q_i       (cols 320..383)
@@ -22,7 +22,7 @@ namespace plm {
 
 constexpr int AB_T = 128;   // tile edge (keys per CTA, queries per step)
 constexpr int AB_HD = 64;
-constexpr int AB_CWARPS = 8;     // compute warps: (TMEM lane quarter) x (column half)
+constexpr int AB_CWARPS = 16;    // compute warps: (TMEM lane quarter) x (column quarter)
 constexpr int AB_THREADS = (AB_CWARPS + 2) * 32;  // + MMA issuer warp + TMA producer warp
 constexpr int AB_STAGES = 3;       // Q_i / dO_i ring
 constexpr int AB_TILE = AB_T * AB_HD * 2;  // 16 KB
@@ -291,145 +291,128 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------ compute warps (8): warp = (lane quarter, column half)
+    // ------------------------------------------------------------ compute warps (16): warp = (lane quarter, column quarter)
+    // Four warps per scheduler: TMEM / shared-memory / MUFU latencies of one warp hide behind the other three.
     const int quarter = warp & 3;
-    const int half = warp >> 2;              // query columns [64*half, 64*half+64) of S^T / dP^T; hd cols [32*half,+32) of dQ/dK/dV
+    const int cq = warp >> 2;                // query columns [32*cq, +32) of S^T / dP^T; hd cols [16*cq, +16) of dQ/dK/dV
     const int r = quarter * 32 + lane;       // key row within the tile (S^T lane) / query row within the tile (dQ lane)
     const int kj = j * AB_T + r;             // key position
-    const int ct = threadIdx.x;              // 0..255
+    const int ct = threadIdx.x;              // 0..511
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const int64_t vec_base = (static_cast<int64_t>(b) * H + h) * T;
 
-    // per-query vectors of a step: threads 0..127 fetch lse & delta, threads 128..255 fetch seg_start
-    auto fetch = [&](int i, float& f0, float& f1, int32_t& g0) {
+    // per-query vectors of a step: threads 0..127 fetch lse, 128..255 delta, 256..383 seg_start
+    auto fetch = [&](int i) -> uint32_t {
       const int q = i * AB_T + (ct & 127);
       const bool ok = q < T;
-      if (ct < 128) {
-        f0 = ok ? lse[vec_base + q] * 1.4426950408889634f : 0.f;
-        f1 = ok ? delta[vec_base + q] : 0.f;
-      } else {
-        g0 = ok ? (seg_start ? seg_start[seq0 + q] : 0) : 0x7fffffff;  // q >= T: nothing allowed
-      }
+      if (ct < 128) return __float_as_uint(ok ? lse[vec_base + q] * 1.4426950408889634f : 0.f);
+      if (ct < 256) return __float_as_uint(ok ? delta[vec_base + q] : 0.f);
+      if (ct < 384) return static_cast<uint32_t>(ok ? (seg_start ? seg_start[seq0 + q] : 0) : 0x7fffffff);
+      return 0u;
     };
-    auto publish = [&](int st, float f0, float f1, int32_t g0) {
-      if (ct < 128) {
-        sLse[st * AB_T + ct] = f0;
-        sDelta[st * AB_T + ct] = f1;
-      } else {
-        sSeg[st * AB_T + ct - 128] = g0;
-      }
+    auto publish = [&](int st, uint32_t v) {
+      if (ct < 128) sLse[st * AB_T + ct] = __uint_as_float(v);
+      else if (ct < 256) sDelta[st * AB_T + ct - 128] = __uint_as_float(v);
+      else if (ct < 384) sSeg[st * AB_T + ct - 256] = static_cast<int32_t>(v);
     };
-    auto dq_flush = [&](int i_tile) {  // dQ of query tile i_tile: lane r now means QUERY row r; 32 head-dim cols/thread
-      float* dst = dq_acc + (seq0 + i_tile * AB_T + r) * d + h * AB_HD + half * 32;
+    auto dq_flush = [&](int i_tile) {  // dQ of query tile i_tile: lane r now means QUERY row r; 16 head-dim cols/thread
+      float* dst = dq_acc + (seq0 + i_tile * AB_T + r) * d + h * AB_HD + cq * 16;
       const bool dq_ok = i_tile * AB_T + r < T;
-      uint32_t t[32];
-      tmem_ld32(tDQ + lane_off + half * 32, t);
+      uint32_t t[16];
+      tmem_ld16(tDQ + lane_off + cq * 16, t);
       tmem_ld_wait();
       if (dq_ok) {
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4)
+        for (int q4 = 0; q4 < 4; ++q4)
           red_add_f32x4(dst + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
                         __uint_as_float(t[4 * q4 + 2]), __uint_as_float(t[4 * q4 + 3]));
       }
     };
-    {
-      float f0 = 0.f, f1 = 0.f;
-      int32_t g0 = 0;
-      fetch(j, f0, f1, g0);
-      publish(0, f0, f1, g0);
-    }
+    publish(0, fetch(j));
 
     for (int it = 0; it < n_it; ++it) {
       const int i = j + it;
       const int st = it & 1;
       named_bar_sync(1, AB_CWARPS * 32);  // vectors of this step visible; everyone is done with the other buffer
-      float nf0 = 0.f, nf1 = 0.f;
-      int32_t ng0 = 0;
-      if (it + 1 < n_it) fetch(i + 1, nf0, nf1, ng0);  // prefetch: latency hidden behind this step's work
-      const float* lse2 = sLse + st * AB_T + half * 64;
-      const float* dl = sDelta + st * AB_T + half * 64;
-      const int32_t* sg = sSeg + st * AB_T + half * 64;
-      const int qpos0 = i * AB_T + half * 64;
+      uint32_t nvec = 0;
+      if (it + 1 < n_it) nvec = fetch(i + 1);  // prefetch: latency hidden behind this step's work
+      const float* lse2 = sLse + st * AB_T + cq * 32;
+      const float* dl = sDelta + st * AB_T + cq * 32;
+      const int32_t* sg = sSeg + st * AB_T + cq * 32;
+      const int qpos0 = i * AB_T + cq * 32;
       const bool need_mask = (i == j) || (sSeg[st * AB_T + AB_T - 1] > j * AB_T);
 
-      // ---- P^T (64 query columns per thread): registers for dS^T, packed bf16 pairs into tensor memory for dV
+      // ---- P^T (32 query columns per thread): registers for dS^T, packed bf16 pairs into tensor memory for dV
       mbar_wait(s_full, it & 1);
       tc_fence_after();
-      float p[2][32];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      float p[32];
+      {
         uint32_t t[32];
-        tmem_ld32(tS + lane_off + half * 64 + c * 32, t);
+        tmem_ld32(tS + lane_off + cq * 32, t);
         tmem_ld_wait();
         if (need_mask)
-          bwd_p_chunk<true>(t, p[c], lse2 + c * 32, sg + c * 32, kj, qpos0 + c * 32, scale_log2);
+          bwd_p_chunk<true>(t, p, lse2, sg, kj, qpos0, scale_log2);
         else
-          bwd_p_chunk<false>(t, p[c], lse2 + c * 32, sg + c * 32, kj, qpos0 + c * 32, scale_log2);
-      }
-      {
-        uint32_t w[32];
+          bwd_p_chunk<false>(t, p, lse2, sg, kj, qpos0, scale_log2);
+        uint32_t w[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          w[e] = pack_bf16x2(p[0][2 * e], p[0][2 * e + 1]);
-          w[16 + e] = pack_bf16x2(p[1][2 * e], p[1][2 * e + 1]);
-        }
-        tmem_st32(tP + lane_off + half * 32, w);
+        for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(p[2 * e], p[2 * e + 1]);
+        tmem_st16(tP + lane_off + cq * 16, w);
         tmem_st_wait();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
 
-      // ---- dQ of the previous step; its completion also means dK/dQ MMAs no longer read the dS^T buffer
+      // ---- dS^T = P^T o (dP^T - delta)      (the softmax scale is applied once, in the dK / dQ epilogues)
+      mbar_wait(dp_full, it & 1);
+      tc_fence_after();
+      {
+        uint32_t t[32];
+        tmem_ld32(tDP + lane_off + cq * 32, t);
+        tmem_ld_wait();
+        float ds[32];
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 dv = *reinterpret_cast<const float4*>(dl + q4 * 4);
+          ds[4 * q4 + 0] = p[4 * q4 + 0] * (__uint_as_float(t[4 * q4 + 0]) - dv.x);
+          ds[4 * q4 + 1] = p[4 * q4 + 1] * (__uint_as_float(t[4 * q4 + 1]) - dv.y);
+          ds[4 * q4 + 2] = p[4 * q4 + 2] * (__uint_as_float(t[4 * q4 + 2]) - dv.z);
+          ds[4 * q4 + 3] = p[4 * q4 + 3] * (__uint_as_float(t[4 * q4 + 3]) - dv.w);
+        }
+        // the previous step's dK/dQ MMAs must be done reading the dS^T buffer before it is overwritten
+        if (it > 0) mbar_wait(dq_full, (it - 1) & 1);
+        store_bf16_row32(sDS + (cq >> 1) * AB_TILE + r * 128, r, (cq & 1) * 4, ds);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_ready);
+
+      // ---- dQ of the previous step (after the hand-off: the red.adds drain while the tensor pipe runs dK_it)
       if (it > 0) {
-        mbar_wait(dq_full, (it - 1) & 1);
         tc_fence_after();
         dq_flush(i - 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_empty);
       }
-
-      // ---- dS^T = P^T o (dP^T - delta)      (the softmax scale is applied once, in the dK / dQ epilogues)
-      mbar_wait(dp_full, it & 1);
-      tc_fence_after();
-      uint8_t* dsrow = sDS + half * AB_TILE + r * 128;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t t[32];
-        tmem_ld32(tDP + lane_off + half * 64 + c * 32, t);
-        tmem_ld_wait();
-        float ds[32];
-#pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          const float4 dv = *reinterpret_cast<const float4*>(dl + c * 32 + q4 * 4);
-          ds[4 * q4 + 0] = p[c][4 * q4 + 0] * (__uint_as_float(t[4 * q4 + 0]) - dv.x);
-          ds[4 * q4 + 1] = p[c][4 * q4 + 1] * (__uint_as_float(t[4 * q4 + 1]) - dv.y);
-          ds[4 * q4 + 2] = p[c][4 * q4 + 2] * (__uint_as_float(t[4 * q4 + 2]) - dv.z);
-          ds[4 * q4 + 3] = p[c][4 * q4 + 3] * (__uint_as_float(t[4 * q4 + 3]) - dv.w);
-        }
-        store_bf16_row32(dsrow, r, c * 4, ds);
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ds_ready);
-      if (it + 1 < n_it) publish(st ^ 1, nf0, nf1, ng0);
+      if (it + 1 < n_it) publish(st ^ 1, nvec);
     }
 
-    // ---- tail: dQ of the last step, then dV / dK of this key tile (32 head-dim columns per thread)
+    // ---- tail: dQ of the last step, then dV / dK of this key tile (16 head-dim columns per thread)
     mbar_wait(dq_full, (n_it - 1) & 1);
     tc_fence_after();
     dq_flush(j + n_it - 1);
     const bool k_ok = kj < T;
     {
-      uint32_t t[32];
-      tmem_ld32(tDV + lane_off + half * 32, t);
+      uint32_t t[16];
+      tmem_ld16(tDV + lane_off + cq * 16, t);
       tmem_ld_wait();
       if (k_ok) {
-        __nv_bfloat16* dv_out = dqkv + (krow0 + r) * (3 * d) + 2 * d + h * AB_HD + half * 32;
+        __nv_bfloat16* dv_out = dqkv + (krow0 + r) * (3 * d) + 2 * d + h * AB_HD + cq * 16;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           uint4 v;
           v.x = pack_bf16x2(__uint_as_float(t[8 * g + 0]), __uint_as_float(t[8 * g + 1]));
           v.y = pack_bf16x2(__uint_as_float(t[8 * g + 2]), __uint_as_float(t[8 * g + 3]));
@@ -440,18 +423,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
     }
     {
-      uint32_t t[32];
-      tmem_ld32(tDK + lane_off + half * 32, t);
+      uint32_t t[16];
+      tmem_ld16(tDK + lane_off + cq * 16, t);
       tmem_ld_wait();
       if (k_ok) {
-        float v[32];
+        float v[16];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(t[e]) * scale;
+        for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(t[e]) * scale;
         if (rope) {  // rotate back: transpose of models/embeddings.py:15-30
           const float4* tab =
-              reinterpret_cast<const float4*>(rope + (static_cast<int64_t>(kj) * (AB_HD >> 1) + half * 16) * 2);
+              reinterpret_cast<const float4*>(rope + (static_cast<int64_t>(kj) * (AB_HD >> 1) + cq * 8) * 2);
 #pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
+          for (int q4 = 0; q4 < 4; ++q4) {
             const float4 cs = __ldg(tab + q4);
             const float x0 = v[4 * q4 + 0], x1 = v[4 * q4 + 1], y0 = v[4 * q4 + 2], y1 = v[4 * q4 + 3];
             v[4 * q4 + 0] = x0 * cs.x + x1 * cs.y;
@@ -460,9 +443,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             v[4 * q4 + 3] = y1 * cs.z - y0 * cs.w;
           }
         }
-        __nv_bfloat16* dk_out = dqkv + (krow0 + r) * (3 * d) + d + h * AB_HD + half * 32;
+        __nv_bfloat16* dk_out = dqkv + (krow0 + r) * (3 * d) + d + h * AB_HD + cq * 16;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < 2; ++g) {
           uint4 o;
           o.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
           o.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
@@ -489,6 +472,7 @@ extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, 
                             float* dq_acc, int32_t B, int32_t T, int32_t H, int32_t hd, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(qkv);
   PLM_REQUIRE(qkv && out && dout && lse && dqkv && delta && dq_acc, "attn_bwd: null pointer");
   PLM_REQUIRE(B > 0 && T > 0 && H > 0, "attn_bwd: bad size");
   if (hd != AB_HD) return fail(PLM_ERR_UNSUPPORTED, "attn_bwd: head_dim %d unsupported (need 64)", hd);

@@ -289,6 +289,7 @@ extern "C" int plm_attn_fwd(const void* qkv, const int32_t* seg_start, void* out
                             int32_t H, int32_t hd, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(qkv);
   PLM_REQUIRE(qkv && out && lse, "attn_fwd: null pointer");
   PLM_REQUIRE(B > 0 && T > 0 && H > 0, "attn_fwd: bad size");
   if (hd != ATT_HD) return fail(PLM_ERR_UNSUPPORTED, "attn_fwd: head_dim %d unsupported (need 64)", hd);

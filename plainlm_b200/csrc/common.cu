@@ -34,6 +34,37 @@ int sm_count() {
   return cached[dev];
 }
 
+// ---- driver entry points (resolved once through the runtime; no link-time dependency on libcuda)
+typedef CUresult (*CtxGetCurrentFn)(CUcontext*);
+typedef CUresult (*CtxSetCurrentFn)(CUcontext);
+typedef CUresult (*PointerGetAttributeFn)(void*, CUpointer_attribute, CUdeviceptr);
+
+static void* driver_fn(const char* name) {
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return p;
+}
+
+int ensure_context(const void* device_ptr) {
+  // Calls may arrive on a thread that has no current CUDA context yet (the autograd engine's worker thread sets its
+  // device lazily).  Bind the context that owns the pointer — never device 0 by default: ranks > 0 own other GPUs.
+  static CtxGetCurrentFn get_cur = reinterpret_cast<CtxGetCurrentFn>(driver_fn("cuCtxGetCurrent"));
+  static CtxSetCurrentFn set_cur = reinterpret_cast<CtxSetCurrentFn>(driver_fn("cuCtxSetCurrent"));
+  static PointerGetAttributeFn ptr_attr = reinterpret_cast<PointerGetAttributeFn>(driver_fn("cuPointerGetAttribute"));
+  if (!get_cur || !set_cur || !ptr_attr) return fail(PLM_ERR_CUDA, "CUDA driver entry points unavailable");
+  CUcontext cur = nullptr;
+  if (get_cur(&cur) == CUDA_SUCCESS && cur != nullptr) return PLM_OK;
+  CUcontext owner = nullptr;
+  CUresult r = ptr_attr(&owner, CU_POINTER_ATTRIBUTE_CONTEXT, reinterpret_cast<CUdeviceptr>(device_ptr));
+  if (r != CUDA_SUCCESS || owner == nullptr)
+    return fail(PLM_ERR_INVALID, "pointer %p is not a device pointer of any CUDA context (%d)", device_ptr, (int)r);
+  r = set_cur(owner);
+  if (r != CUDA_SUCCESS) return fail(PLM_ERR_CUDA, "cuCtxSetCurrent failed (%d)", (int)r);
+  return PLM_OK;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -17,11 +17,22 @@ int check_launch(const char* what);
 
 int sm_count();
 
+// Makes the CUDA context that owns `device_ptr` current on the calling thread if the thread has none.
+int ensure_context(const void* device_ptr);
+
 // Encodes a 2-D bf16 tensor map: tensor is [rows, cols] row-major with leading dimension `ld` (elements);
 // a box is [box_rows, box_cols] elements, 128-byte swizzle (box_cols * 2 bytes must be 128).
 // Out-of-bounds elements are zero-filled by the hardware.
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
+
+#define PLM_ENSURE_CONTEXT(ptr)                            \
+  do {                                                    \
+    if ((ptr) != nullptr) {                               \
+      const int rc_ = ::plm::ensure_context(ptr);         \
+      if (rc_ != PLM_OK) return rc_;                      \
+    }                                                     \
+  } while (0)
 
 #define PLM_REQUIRE(cond, ...)                                  \
   do {                                                          \

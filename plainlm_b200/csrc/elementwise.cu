@@ -189,6 +189,7 @@ extern "C" {
 int plm_swiglu_fwd(const void* u, void* h, int64_t rows, int32_t F, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(u);
   PLM_REQUIRE(u && h && rows >= 0 && F > 0, "swiglu_fwd: bad argument");
   PLM_REQUIRE(F % 8 == 0 && aligned16(u) && aligned16(h), "swiglu_fwd: F %% 8 and 16-byte alignment required");
   if (rows == 0) return PLM_OK;
@@ -201,6 +202,7 @@ int plm_swiglu_fwd(const void* u, void* h, int64_t rows, int32_t F, plm_stream_t
 int plm_swiglu_bwd(const void* dh, const void* u, void* du, int64_t rows, int32_t F, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(u);
   PLM_REQUIRE(dh && u && du && rows >= 0 && F > 0, "swiglu_bwd: bad argument");
   PLM_REQUIRE(F % 8 == 0 && aligned16(u) && aligned16(dh) && aligned16(du),
               "swiglu_bwd: F %% 8 and 16-byte alignment required");
@@ -215,6 +217,7 @@ int plm_embed_fwd(const int64_t* ids, const float* W, float* x, int64_t rows, in
                   plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(W);
   PLM_REQUIRE(ids && W && x && rows >= 0 && d > 0 && vocab > 0, "embed_fwd: bad argument");
   PLM_REQUIRE(d % 4 == 0 && aligned16(W) && aligned16(x), "embed_fwd: d %% 4 and 16-byte alignment required");
   if (rows == 0) return PLM_OK;
@@ -227,6 +230,7 @@ int plm_embed_bwd(const int64_t* ids, const float* dx, float* dW, int64_t rows, 
                   plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(dx);
   PLM_REQUIRE(ids && dx && dW && rows >= 0 && d > 0 && vocab > 0, "embed_bwd: bad argument");
   PLM_REQUIRE(d % 4 == 0 && aligned16(dW) && aligned16(dx), "embed_bwd: d %% 4 and 16-byte alignment required");
   if (rows == 0) return PLM_OK;
@@ -238,6 +242,7 @@ int plm_embed_bwd(const int64_t* ids, const float* dx, float* dW, int64_t rows, 
 int plm_cast_f32_bf16(const float* src, void* dst, int64_t n, float scale, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(src);
   PLM_REQUIRE(src && dst && n >= 0, "cast_f32_bf16: bad argument");
   PLM_REQUIRE(aligned16(src) && aligned16(dst), "cast_f32_bf16: misaligned pointer");
   if (n == 0) return PLM_OK;
@@ -252,6 +257,7 @@ int plm_cast_f32_bf16(const float* src, void* dst, int64_t n, float scale, plm_s
 int plm_cast_bf16_f32(const void* src, float* dst, int64_t n, float scale, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(src);
   PLM_REQUIRE(src && dst && n >= 0, "cast_bf16_f32: bad argument");
   PLM_REQUIRE(aligned16(src) && aligned16(dst), "cast_bf16_f32: misaligned pointer");
   if (n == 0) return PLM_OK;
@@ -267,6 +273,7 @@ int plm_rope_qk(void* qkv, const float* rope_table, int64_t rows, int32_t T, int
                 plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(qkv);
   PLM_REQUIRE(qkv && rope_table && rows >= 0 && T > 0 && H > 0 && hd > 0, "rope_qk: bad argument");
   PLM_REQUIRE(hd % 8 == 0 && aligned16(qkv) && aligned16(rope_table), "rope_qk: hd %% 8 and alignment required");
   PLM_REQUIRE(dir == 1 || dir == -1, "rope_qk: dir must be +1 or -1");
@@ -281,6 +288,7 @@ int plm_seg_start_from_lengths(const int32_t* lengths, const int32_t* offsets, i
                                int32_t T, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(lengths);
   PLM_REQUIRE(lengths && offsets && seg_start && B > 0 && T > 0, "seg_start: bad argument");
   seg_start_kernel<<<B, 256, 0, stream>>>(lengths, offsets, seg_start, T);
   return check_launch("seg_start");

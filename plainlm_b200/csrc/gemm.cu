@@ -303,6 +303,7 @@ static int env_int(const char* name, int dflt) {
 extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(a ? a->A : nullptr);
   PLM_REQUIRE(a != nullptr, "gemm: null args");
   PLM_REQUIRE(a->A && a->B && a->C, "gemm: null operand");
   PLM_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "gemm: non-positive size M=%lld N=%lld K=%lld", (long long)a->M,

@@ -289,6 +289,7 @@ int plm_ce_fwd_bwd(void* logits, const int64_t* targets, float* row_loss, float*
                    int32_t V, int64_t ldl, float grad_scale, int32_t write_grad, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(logits);
   PLM_REQUIRE(logits && targets && row_loss && row_lse && stats, "ce: null pointer");
   PLM_REQUIRE(rows > 0 && V > 0 && ldl >= V, "ce: bad size");
   PLM_REQUIRE(V % 8 == 0 && ldl % 8 == 0 && aligned16(logits), "ce: V, ldl must be multiples of 8, logits aligned");
@@ -310,6 +311,7 @@ int plm_ce_fwd_bwd(void* logits, const int64_t* targets, float* row_loss, float*
 int plm_sumsq(const float* g, int64_t n, float* workspace, float* out, int32_t accumulate, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(g);
   static_assert(SUMSQ_BLOCKS <= PLM_SUMSQ_WORKSPACE, "workspace too small");
   PLM_REQUIRE(g && workspace && out && n >= 0, "sumsq: bad argument");
   PLM_REQUIRE(aligned16(g), "sumsq: misaligned pointer");
@@ -325,6 +327,7 @@ int plm_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, i
                    float max_norm, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(p);
   PLM_REQUIRE(p && g && m && v && n >= 0, "adamw: bad argument");
   PLM_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "adamw: misaligned pointer");
   PLM_REQUIRE(!p_bf16 || (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0, "adamw: misaligned bf16 shadow");
@@ -349,6 +352,7 @@ int plm_signsgd_step(float* p, const float* g, float* m, void* p_bf16, int64_t n
                      plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(p);
   PLM_REQUIRE(p && g && m && n >= 0, "signsgd: bad argument");
   PLM_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m), "signsgd: misaligned pointer");
   PLM_REQUIRE(!p_bf16 || (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0, "signsgd: misaligned bf16 shadow");

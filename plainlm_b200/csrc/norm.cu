@@ -189,6 +189,7 @@ int plm_rmsnorm_fwd(const float* x, const float* w, void* y_bf16, float* rstd, i
                     plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(x);
   PLM_REQUIRE(x && w && y_bf16 && rstd, "rmsnorm_fwd: null pointer");
   PLM_REQUIRE(rows >= 0 && d > 0, "rmsnorm_fwd: bad size");
   PLM_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y_bf16), "rmsnorm_fwd: misaligned pointer");
@@ -207,6 +208,7 @@ int plm_rmsnorm_bwd(const void* dy_bf16, const float* x, const float* w, const f
                     plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(x);
   PLM_REQUIRE(dy_bf16 && x && w && rstd && dx_out && dw_partial, "rmsnorm_bwd: null pointer");
   PLM_REQUIRE(rows > 0 && d > 0, "rmsnorm_bwd: bad size");
   PLM_REQUIRE(aligned16(dy_bf16) && aligned16(x) && aligned16(w) && aligned16(dx_out) && aligned16(dw_partial) &&
@@ -223,6 +225,7 @@ int plm_rmsnorm_bwd(const void* dy_bf16, const float* x, const float* w, const f
 int plm_colsum_accum(const float* partial, float* dw, int32_t nblocks, int32_t d, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(partial);
   PLM_REQUIRE(partial && dw && nblocks > 0 && d > 0, "colsum_accum: bad argument");
   colsum_accum_kernel<<<(d + 31) / 32, 256, 0, stream>>>(partial, dw, nblocks, d);
   return check_launch("colsum_accum");

@@ -370,3 +370,26 @@ def test_optimizers_against_reference_fixture(golden_dir):
     assert sorted(opt.state[p].keys()) == f['state_keys']
     sd = opt.state_dict()
     assert sorted(sd['state'][0].keys()) == f['state_keys']
+
+
+def test_first_call_from_autograd_thread_in_fresh_process():
+  """Regression: the autograd worker thread may have no current CUDA context when a backward kernel is the first thing
+  it runs; the C ABI must bind the context that owns its pointers (and never default to device 0)."""
+  import subprocess
+  import sys
+
+  code = (
+    'import torch, sys\n'
+    f'sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})\n'
+    'from plainlm_b200.models import functional as PF\n'
+    'x = torch.randn(64, 128, device="cuda", dtype=torch.bfloat16, requires_grad=True)\n'
+    'w = torch.randn(256, 128, device="cuda", requires_grad=True)\n'
+    'y = PF.linear(x, w)\n'
+    'y.backward(torch.ones_like(y))\n'
+    'torch.cuda.synchronize()\n'
+    'ref = torch.ones(64, 256, device="cuda") @ w.detach().bfloat16().float()\n'
+    'assert (x.grad.float() - ref).abs().max() <= 2e-2 * ref.abs().max()\n'
+    'print("OK")\n'
+  )
+  res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300)
+  assert res.returncode == 0 and 'OK' in res.stdout, res.stderr[-2000:]
