@@ -175,6 +175,10 @@ int plm_cast_bf16_f32(const void* src, float* dst, int64_t n, float scale, plm_s
 int plm_seg_start_from_lengths(const int32_t* lengths, const int32_t* offsets, int32_t* seg_start, int32_t B,
                                int32_t T, plm_stream_t stream);
 
+/* Diagnostics: per-phase cycle counters of the attention-backward kernel (HOST pointer, n <= 32).  All zeros unless the
+ * library was built with -DPLM_ATTN_TIMING; synchronises the device. */
+int plm_debug_counters(unsigned long long* out, int32_t n, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

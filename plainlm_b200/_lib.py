@@ -53,6 +53,7 @@ SIGNATURES = {
   'plm_cast_f32_bf16': (c_int32, [_P, _P, _I64, _F, _P]),
   'plm_cast_bf16_f32': (c_int32, [_P, _P, _I64, _F, _P]),
   'plm_seg_start_from_lengths': (c_int32, [_P, _P, _P, _I32, _I32, _P]),
+  'plm_debug_counters': (c_int32, [ctypes.POINTER(ctypes.c_ulonglong), _I32, _I32]),
 }  # fmt: skip
 
 _lib = None

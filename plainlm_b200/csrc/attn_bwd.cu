@@ -1,18 +1,18 @@
 // Flash-attention backward on tcgen05 (backward of models/transformer.py:53-63, reached from engine/engine.py:120).
 //
-// One CTA per (128-key tile j, head, batch), looping over the query tiles i >= j that can see it. 576 threads:
+// One CTA per (128-key tile j, head, batch), looping over the query tiles i >= j that can see it. 640 threads:
 //   warps 0..15 compute: warp = (TMEM lane quarter, column quarter); a thread owns 32 columns of key row r of the
 //               transposed score tile — four warps per scheduler so TMEM / smem / MUFU latencies overlap
-//   warp 16     MMA issuer (one thread, all tcgen05.mma)      warp 17 TMA producer (K,V once; Q_i,dO_i 3-stage ring)
+//   warps 16-18 MMA issuers (S^T,dP^T | dV | dK,dQ: one thread each)   warp 19 TMA producer (K,V; Q_i,dO_i 3-stage ring)
 // Five GEMMs per (j, i) pair, all on the tensor core, all 512 TMEM columns in use:
 //   S^T  = K Q_i^T        (cols   0..127)      dP^T = V dO_i^T       (cols 128..255)
 //   dV  += P^T dO_i       (cols 256..319)      dK  += dS^T Q_i       (cols 320..383)
 //   dQ_i = dS K           (cols 384..447) -> fp32 red.add into dq_acc (finalised by dq_finalize_kernel)
 //   P^T as packed bf16    (cols 448..511) -> A operand of the dV GEMM read straight from tensor memory
 // dS^T is written once to swizzled smem as a K-major A operand (dK) and re-read MN-major for the dQ GEMM; Q_i / dO_i /
-// K are consumed as MN-major B operands straight from their TMA boxes — no transposes anywhere.  The issue order
-// (dV_i, S_{i+1} | dK_i, dQ_i, dP_{i+1}) keeps the tensor pipe busy while the compute warps do the exp / dS math of
-// the neighbouring step.  dK and dQ are rotated back through RoPE in the epilogues.
+// K are consumed as MN-major B operands straight from their TMA boxes — no transposes anywhere.  S^T / dP^T of step
+// i+1 are issued as soon as the compute warps have READ step i's tiles out of tensor memory, so the tensor pipe works
+// on the neighbouring step while the exp / dS math runs.  dK and dQ are rotated back through RoPE in the epilogues.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -23,11 +23,15 @@ namespace plm {
 constexpr int AB_T = 128;   // tile edge (keys per CTA, queries per step)
 constexpr int AB_HD = 64;
 constexpr int AB_CWARPS = 16;    // compute warps: (TMEM lane quarter) x (column quarter)
-constexpr int AB_THREADS = (AB_CWARPS + 2) * 32;  // + MMA issuer warp + TMA producer warp
+constexpr int AB_W_MMA_S = AB_CWARPS;       // issues S^T and dP^T
+constexpr int AB_W_MMA_DV = AB_CWARPS + 1;  // issues dV
+constexpr int AB_W_MMA_DKQ = AB_CWARPS + 2; // issues dK and dQ
+constexpr int AB_W_TMA = AB_CWARPS + 3;     // TMA producer
+constexpr int AB_THREADS = (AB_CWARPS + 4) * 32;
 constexpr int AB_STAGES = 3;       // Q_i / dO_i ring
 constexpr int AB_TILE = AB_T * AB_HD * 2;  // 16 KB
 // K, V, (Q,dO) x AB_STAGES, dS^T (2 blocks), vectors (lse2, delta, seg) x2 stages, barriers
-constexpr int AB_VEC_BYTES = 2 * 3 * AB_T * 4;
+constexpr int AB_VEC_BYTES = AB_STAGES * 3 * AB_T * 4;
 constexpr int AB_SMEM = AB_TILE * (2 + 2 * AB_STAGES + 2) + AB_VEC_BYTES + 256;
 
 __device__ __forceinline__ float ex2b(float x) {
@@ -35,6 +39,9 @@ __device__ __forceinline__ float ex2b(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+
+// Diagnostic counters exported through plm_debug_counters (unused in release builds: always zero).
+__device__ unsigned long long g_dbg_counters[32];
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -148,19 +155,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint8_t* sQ = smem + 2 * AB_TILE;                    // [AB_STAGES]
   uint8_t* sDO = smem + (2 + AB_STAGES) * AB_TILE;     // [AB_STAGES]
   uint8_t* sDS = smem + (2 + 2 * AB_STAGES) * AB_TILE; // dS^T: 2 blocks (q 0..63 | 64..127), each [128 kv rows x 128 B]
-  float* sLse = reinterpret_cast<float*>(smem + (4 + 2 * AB_STAGES) * AB_TILE);  // [2][128]  lse * log2(e)
-  float* sDelta = sLse + 2 * AB_T;                                                 // [2][128]
-  int32_t* sSeg = reinterpret_cast<int32_t*>(sDelta + 2 * AB_T);                   // [2][128]
+  float* sLse = reinterpret_cast<float*>(smem + (4 + 2 * AB_STAGES) * AB_TILE);  // [AB_STAGES][128]  lse * log2(e)
+  float* sDelta = sLse + AB_STAGES * AB_T;                                         // [AB_STAGES][128]
+  int32_t* sSeg = reinterpret_cast<int32_t*>(sDelta + AB_STAGES * AB_T);           // [AB_STAGES][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (4 + 2 * AB_STAGES) * AB_TILE + AB_VEC_BYTES);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;                // [AB_STAGES]
+  uint64_t* qdo_full = bars + 1;                // [AB_STAGES]  TMA bytes of Q_i, dO_i + the 32 staging lanes
   uint64_t* qdo_empty = bars + 1 + AB_STAGES;   // [AB_STAGES]
-  uint64_t* s_full = bars + 1 + 2 * AB_STAGES;
-  uint64_t* dp_full = s_full + 1;
-  uint64_t* p_ready = s_full + 2;
-  uint64_t* ds_ready = s_full + 3;
-  uint64_t* dq_full = s_full + 4;
-  uint64_t* dq_empty = s_full + 5;
+  uint64_t* s_full = bars + 1 + 2 * AB_STAGES;  // S^T and dP^T of a step are in tensor memory
+  uint64_t* pds_ready = s_full + 1;             // P^T (tensor memory) and dS^T (smem) of a step are written
+  uint64_t* dq_full = s_full + 2;               // dK/dQ MMAs of a step complete
+  uint64_t* dq_empty = s_full + 3;              // dQ of a step has been read out of tensor memory
+  uint64_t* sdp_free = s_full + 4;              // compute warps have read S^T and dP^T out of tensor memory
+  uint64_t* dv_done = s_full + 5;               // dV MMAs of a step complete: the P^T columns may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
 
   if ((smem_u32(smem) & 1023u) != 0) return;
@@ -188,18 +195,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     tma_prefetch_desc(&tmDO);
     mbar_init(kv_full, 1);
     for (int s = 0; s < AB_STAGES; ++s) {
-      mbar_init(&qdo_full[s], 1);
-      mbar_init(&qdo_empty[s], 1);
+      mbar_init(&qdo_full[s], 1 + 32);  // expect_tx arrive + one arrive per staging lane
+      mbar_init(&qdo_empty[s], 2);      // released by the dV issuer and by the dK/dQ issuer
     }
     mbar_init(s_full, 1);
-    mbar_init(dp_full, 1);
-    mbar_init(p_ready, AB_CWARPS);
-    mbar_init(ds_ready, AB_CWARPS);
+    mbar_init(pds_ready, AB_CWARPS);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, AB_CWARPS);
+    mbar_init(sdp_free, AB_CWARPS);
+    mbar_init(dv_done, 1);
     fence_barrier_init();
   }
-  if (warp == AB_CWARPS) {
+  if (warp == AB_W_MMA_S) {
     tmem_alloc<512>(tmem_slot);
     tmem_relinquish();
   }
@@ -211,110 +218,118 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
                  tDQ = tmem_base + 384, tP = tmem_base + 448;
 
-  if (warp == AB_CWARPS + 1) {
-    // ------------------------------------------------------------ TMA producer
+  if (warp == AB_W_TMA) {
+    // ------------------------------------------------------------ producer warp: lane 0 drives TMA (K,V once; Q_i,dO_i
+    // ring), all 32 lanes stage the per-query vectors (lse*log2e, delta, seg_start) of the step next to its tiles.
     if (lane == 0) {
       mbar_arrive_expect_tx(kv_full, 2 * AB_TILE);
       tma_load_2d(sK, &tmQKV, kv_full, d + h * AB_HD, static_cast<int>(krow0));
       tma_load_2d(sV, &tmQKV, kv_full, 2 * d + h * AB_HD, static_cast<int>(krow0));
-      for (int it = 0; it < n_it; ++it) {
-        const int st = it % AB_STAGES, use = it / AB_STAGES;
-        mbar_wait(&qdo_empty[st], (use & 1) ^ 1);
+    }
+    const int64_t vec_base = (static_cast<int64_t>(b) * H + h) * T;
+    int st = 0;
+    for (int it = 0; it < n_it; ++it) {
+      mbar_wait(&qdo_empty[st], ((it / AB_STAGES) & 1) ^ 1);
+      if (lane == 0) {
         const int qr = static_cast<int>(seq0 + (j + it) * AB_T);
         mbar_arrive_expect_tx(&qdo_full[st], 2 * AB_TILE);
         tma_load_2d(sQ + st * AB_TILE, &tmQKV, &qdo_full[st], h * AB_HD, qr);
         tma_load_2d(sDO + st * AB_TILE, &tmDO, &qdo_full[st], h * AB_HD, qr);
       }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qq = e * 32 + lane;
+        const int q = (j + it) * AB_T + qq;
+        const bool ok = q < T;
+        sLse[st * AB_T + qq] = ok ? lse[vec_base + q] * 1.4426950408889634f : 0.f;
+        sDelta[st * AB_T + qq] = ok ? delta[vec_base + q] : 0.f;
+        sSeg[st * AB_T + qq] = ok ? (seg_start ? seg_start[seq0 + q] : 0) : 0x7fffffff;  // q >= T: nothing allowed
+      }
+      mbar_arrive(&qdo_full[st]);  // release: the vectors are visible to whoever acquires the barrier
+      if (++st == AB_STAGES) st = 0;
     }
-  } else if (warp == AB_CWARPS) {
+  } else if (warp == AB_W_MMA_S) {
+    // ------------------------------------------------------------ MMA issuer 1: S^T = K Q^T and dP^T = V dO^T.
+    // Three issuing warps keep the issue rate above the 32..64-cycle MMAs; S^T / dP^T of step it+1 only wait for the
+    // previous tiles to be READ out of tensor memory (sdp_free), not for the math on them.
     if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer.  Tensor-pipe order per step `it`:
-      //   dV_it (needs P^T_it) , S^T_{it+1} | dK_it , dQ_it (need dS^T_it) , dP^T_{it+1}
-      // so the exp-heavy half of step it+1 overlaps the dK/dQ/dP MMAs of step it, and its dS half overlaps dV/S.
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // K-major x K-major, N = 128 queries
-      constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);   // A K-major (smem or TMEM), B MN-major, N = 64
+      mbar_wait(kv_full, 0);
+      // descriptors are built once; per K-step only the 14-bit start-address field advances (tight issue loop)
+      const uint64_t k_desc = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t v_desc = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
+      const uint64_t q_desc0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t do_desc0 = make_smem_desc_sw128(smem_u32(sDO), 16, 1024);
+      int st = 0;
+      for (int it = 0; it < n_it; ++it) {
+        const uint64_t q_desc = q_desc0 + st * (AB_TILE >> 4), do_desc = do_desc0 + st * (AB_TILE >> 4);
+        mbar_wait(&qdo_full[st], (it / AB_STAGES) & 1);
+        if (it > 0) mbar_wait(sdp_free, (it - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < AB_HD / 16; ++k) {
+          umma_ss(tS, k_desc + k * 2, q_desc + k * 2, idesc_s, k > 0 ? 1u : 0u);
+          umma_ss(tDP, v_desc + k * 2, do_desc + k * 2, idesc_s, k > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        if (++st == AB_STAGES) st = 0;
+      }
+    }
+  } else if (warp == AB_W_MMA_DV) {
+    // ------------------------------------------------------------ MMA issuer 2: dV += P^T dO (A = P^T from tensor memory)
+    if (lane == 0) {
+      constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);   // A K-major (TMEM), B MN-major, N = 64
+      const uint64_t do_desc0 = make_smem_desc_sw128(smem_u32(sDO), AB_TILE, 1024);
+      int st = 0;
+      for (int it = 0; it < n_it; ++it) {
+        const uint64_t do_desc = do_desc0 + st * (AB_TILE >> 4);
+        mbar_wait(pds_ready, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < AB_T / 16; ++k)
+          umma_ts(tDV, tP + k * 8, do_desc + k * (2048 >> 4), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(dv_done);
+        umma_commit(&qdo_empty[st]);
+        if (++st == AB_STAGES) st = 0;
+      }
+    }
+  } else if (warp == AB_W_MMA_DKQ) {
+    // ------------------------------------------------------------ MMA issuer 3: dK += dS^T Q ; dQ = dS K
+    if (lane == 0) {
+      constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);   // A K-major, B MN-major, N = 64
       constexpr uint32_t idesc_nn = make_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major (dQ)
       mbar_wait(kv_full, 0);
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), ds_addr = smem_u32(sDS);
-      auto issue_s = [&](int it) {
-        const int st = it % AB_STAGES;
-        mbar_wait(&qdo_full[st], (it / AB_STAGES) & 1);
-        tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ + st * AB_TILE);
-#pragma unroll
-        for (int k = 0; k < AB_HD / 16; ++k)
-          umma_ss(tS, make_smem_desc_sw128(k_addr + k * 32, 16, 1024), make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                  idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(s_full);
-      };
-      auto issue_dp = [&](int it) {
-        const int st = it % AB_STAGES;
-        const uint32_t do_addr = smem_u32(sDO + st * AB_TILE);
-#pragma unroll
-        for (int k = 0; k < AB_HD / 16; ++k)
-          umma_ss(tDP, make_smem_desc_sw128(v_addr + k * 32, 16, 1024),
-                  make_smem_desc_sw128(do_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(dp_full);
-      };
-      issue_s(0);
-      issue_dp(0);
+      const uint64_t k_desc_mn = make_smem_desc_sw128(smem_u32(sK), AB_TILE, 1024);
+      const uint64_t ds_desc_k = make_smem_desc_sw128(smem_u32(sDS), 16, 1024);        // K-major view (dK)
+      const uint64_t ds_desc_mn = make_smem_desc_sw128(smem_u32(sDS), AB_TILE, 1024);  // MN-major view (dQ)
+      const uint64_t q_desc0 = make_smem_desc_sw128(smem_u32(sQ), AB_TILE, 1024);
+      int st = 0;
       for (int it = 0; it < n_it; ++it) {
-        const int st = it % AB_STAGES;
-        const uint32_t q_addr = smem_u32(sQ + st * AB_TILE), do_addr = smem_u32(sDO + st * AB_TILE);
-        // ---- dV += P^T dO   (A = P^T from tensor memory: 8 columns per 16-query K-step)
-        mbar_wait(p_ready, it & 1);
+        const uint64_t q_desc = q_desc0 + st * (AB_TILE >> 4);
+        mbar_wait(pds_ready, it & 1);
+        if (it > 0) mbar_wait(dq_empty, (it - 1) & 1);
         tc_fence_after();
+        // dK and dQ interleaved.  dQ: A = dS^T buffer read MN-major (M = queries, 64 per block, blocks AB_TILE apart),
+        // B = K MN-major
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k)
-          umma_ts(tDV, tP + k * 8, make_smem_desc_sw128(do_addr + k * 2048, AB_TILE, 1024), idesc_kn,
+        for (int k = 0; k < AB_T / 16; ++k) {
+          umma_ss(tDK, ds_desc_k + ((k >> 2) * AB_TILE + (k & 3) * 32) / 16, q_desc + k * (2048 >> 4), idesc_kn,
                   (it > 0 || k > 0) ? 1u : 0u);
-        if (it + 1 < n_it) issue_s(it + 1);  // S^T region is free: every compute warp read it before p_ready
-        // ---- dK += dS^T Q ; dQ = dS K
-        mbar_wait(ds_ready, it & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k)
-          umma_ss(tDK, make_smem_desc_sw128(ds_addr + (k >> 2) * AB_TILE + (k & 3) * 32, 16, 1024),
-                  make_smem_desc_sw128(q_addr + k * 2048, AB_TILE, 1024), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
-        if (it > 0) {
-          mbar_wait(dq_empty, (it - 1) & 1);
-          tc_fence_after();
+          umma_ss(tDQ, ds_desc_mn + k * (2048 >> 4), k_desc_mn + k * (2048 >> 4), idesc_nn, k > 0 ? 1u : 0u);
         }
-        // A = dS^T buffer read MN-major (M = queries, 64 per block, blocks AB_TILE apart), B = K MN-major
-#pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k)
-          umma_ss(tDQ, make_smem_desc_sw128(ds_addr + k * 2048, AB_TILE, 1024),
-                  make_smem_desc_sw128(k_addr + k * 2048, AB_TILE, 1024), idesc_nn, k > 0 ? 1u : 0u);
         umma_commit(&qdo_empty[st]);
         umma_commit(dq_full);
-        if (it + 1 < n_it) issue_dp(it + 1);  // dP^T region is free: every compute warp read it before ds_ready
+        if (++st == AB_STAGES) st = 0;
       }
     }
   } else {
     // ------------------------------------------------------------ compute warps (16): warp = (lane quarter, column quarter)
-    // Four warps per scheduler: TMEM / shared-memory / MUFU latencies of one warp hide behind the other three.
     const int quarter = warp & 3;
     const int cq = warp >> 2;                // query columns [32*cq, +32) of S^T / dP^T; hd cols [16*cq, +16) of dQ/dK/dV
     const int r = quarter * 32 + lane;       // key row within the tile (S^T lane) / query row within the tile (dQ lane)
     const int kj = j * AB_T + r;             // key position
-    const int ct = threadIdx.x;              // 0..511
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const int64_t vec_base = (static_cast<int64_t>(b) * H + h) * T;
 
-    // per-query vectors of a step: threads 0..127 fetch lse, 128..255 delta, 256..383 seg_start
-    auto fetch = [&](int i) -> uint32_t {
-      const int q = i * AB_T + (ct & 127);
-      const bool ok = q < T;
-      if (ct < 128) return __float_as_uint(ok ? lse[vec_base + q] * 1.4426950408889634f : 0.f);
-      if (ct < 256) return __float_as_uint(ok ? delta[vec_base + q] : 0.f);
-      if (ct < 384) return static_cast<uint32_t>(ok ? (seg_start ? seg_start[seq0 + q] : 0) : 0x7fffffff);
-      return 0u;
-    };
-    auto publish = [&](int st, uint32_t v) {
-      if (ct < 128) sLse[st * AB_T + ct] = __uint_as_float(v);
-      else if (ct < 256) sDelta[st * AB_T + ct - 128] = __uint_as_float(v);
-      else if (ct < 384) sSeg[st * AB_T + ct - 256] = static_cast<int32_t>(v);
-    };
     auto dq_flush = [&](int i_tile) {  // dQ of query tile i_tile: lane r now means QUERY row r; 16 head-dim cols/thread
       float* dst = dq_acc + (seq0 + i_tile * AB_T + r) * d + h * AB_HD + cq * 16;
       const bool dq_ok = i_tile * AB_T + r < T;
@@ -328,80 +343,73 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                         __uint_as_float(t[4 * q4 + 2]), __uint_as_float(t[4 * q4 + 3]));
       }
     };
-    publish(0, fetch(j));
 
+    int st = 0;
     for (int it = 0; it < n_it; ++it) {
       const int i = j + it;
-      const int st = it & 1;
-      named_bar_sync(1, AB_CWARPS * 32);  // vectors of this step visible; everyone is done with the other buffer
-      uint32_t nvec = 0;
-      if (it + 1 < n_it) nvec = fetch(i + 1);  // prefetch: latency hidden behind this step's work
+      // one hand-off in: tiles of this step are in tensor memory (s_full), its vectors are staged (qdo_full)
+      mbar_wait(&qdo_full[st], (it / AB_STAGES) & 1);
+      mbar_wait(s_full, it & 1);
+      tc_fence_after();
       const float* lse2 = sLse + st * AB_T + cq * 32;
       const float* dl = sDelta + st * AB_T + cq * 32;
       const int32_t* sg = sSeg + st * AB_T + cq * 32;
       const int qpos0 = i * AB_T + cq * 32;
       const bool need_mask = (i == j) || (sSeg[st * AB_T + AB_T - 1] > j * AB_T);
 
-      // ---- P^T (32 query columns per thread): registers for dS^T, packed bf16 pairs into tensor memory for dV
-      mbar_wait(s_full, it & 1);
-      tc_fence_after();
-      float p[32];
-      {
-        uint32_t t[32];
-        tmem_ld32(tS + lane_off + cq * 32, t);
-        tmem_ld_wait();
-        if (need_mask)
-          bwd_p_chunk<true>(t, p, lse2, sg, kj, qpos0, scale_log2);
-        else
-          bwd_p_chunk<false>(t, p, lse2, sg, kj, qpos0, scale_log2);
-        uint32_t w[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(p[2 * e], p[2 * e + 1]);
-        tmem_st16(tP + lane_off + cq * 16, w);
-        tmem_st_wait();
-      }
+      uint32_t ts[32], tdp[32];
+      tmem_ld32(tS + lane_off + cq * 32, ts);
+      tmem_ld32(tDP + lane_off + cq * 32, tdp);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
+      if (lane == 0) mbar_arrive(sdp_free);  // S^T / dP^T of the next step may be issued while we do the math
 
-      // ---- dS^T = P^T o (dP^T - delta)      (the softmax scale is applied once, in the dK / dQ epilogues)
-      mbar_wait(dp_full, it & 1);
-      tc_fence_after();
-      {
-        uint32_t t[32];
-        tmem_ld32(tDP + lane_off + cq * 32, t);
-        tmem_ld_wait();
-        float ds[32];
+      // P^T = exp2(S^T * scale*log2e - lse*log2e), masked;  dS^T = P^T o (dP^T - delta)  (softmax scale applied once,
+      // in the dK / dQ epilogues)
+      float p[32];
+      if (need_mask)
+        bwd_p_chunk<true>(ts, p, lse2, sg, kj, qpos0, scale_log2);
+      else
+        bwd_p_chunk<false>(ts, p, lse2, sg, kj, qpos0, scale_log2);
+      uint32_t w[16];
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          const float4 dv = *reinterpret_cast<const float4*>(dl + q4 * 4);
-          ds[4 * q4 + 0] = p[4 * q4 + 0] * (__uint_as_float(t[4 * q4 + 0]) - dv.x);
-          ds[4 * q4 + 1] = p[4 * q4 + 1] * (__uint_as_float(t[4 * q4 + 1]) - dv.y);
-          ds[4 * q4 + 2] = p[4 * q4 + 2] * (__uint_as_float(t[4 * q4 + 2]) - dv.z);
-          ds[4 * q4 + 3] = p[4 * q4 + 3] * (__uint_as_float(t[4 * q4 + 3]) - dv.w);
-        }
-        // the previous step's dK/dQ MMAs must be done reading the dS^T buffer before it is overwritten
-        if (it > 0) mbar_wait(dq_full, (it - 1) & 1);
-        store_bf16_row32(sDS + (cq >> 1) * AB_TILE + r * 128, r, (cq & 1) * 4, ds);
+      for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(p[2 * e], p[2 * e + 1]);
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const float4 dv = *reinterpret_cast<const float4*>(dl + q4 * 4);
+        p[4 * q4 + 0] *= __uint_as_float(tdp[4 * q4 + 0]) - dv.x;
+        p[4 * q4 + 1] *= __uint_as_float(tdp[4 * q4 + 1]) - dv.y;
+        p[4 * q4 + 2] *= __uint_as_float(tdp[4 * q4 + 2]) - dv.z;
+        p[4 * q4 + 3] *= __uint_as_float(tdp[4 * q4 + 3]) - dv.w;
       }
+      // the previous step's dV MMAs must be done with the P^T columns, its dK/dQ MMAs with the dS^T buffer
+      if (it > 0) {
+        mbar_wait(dv_done, (it - 1) & 1);
+        mbar_wait(dq_full, (it - 1) & 1);
+        tc_fence_after();
+      }
+      tmem_st16(tP + lane_off + cq * 16, w);
+      store_bf16_row32(sDS + (cq >> 1) * AB_TILE + r * 128, r, (cq & 1) * 4, p);
+      tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_ready);
+      if (lane == 0) mbar_arrive(pds_ready);  // one hand-off out
 
-      // ---- dQ of the previous step (after the hand-off: the red.adds drain while the tensor pipe runs dK_it)
+      // dQ of the previous step (the red.adds drain while the tensor pipe runs dV / dK of this step)
       if (it > 0) {
-        tc_fence_after();
         dq_flush(i - 1);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_empty);
       }
-      if (it + 1 < n_it) publish(st ^ 1, nvec);
+      if (++st == AB_STAGES) st = 0;
     }
 
     // ---- tail: dQ of the last step, then dV / dK of this key tile (16 head-dim columns per thread)
     mbar_wait(dq_full, (n_it - 1) & 1);
+    mbar_wait(dv_done, (n_it - 1) & 1);
     tc_fence_after();
     dq_flush(j + n_it - 1);
     const bool k_ok = kj < T;
@@ -459,13 +467,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (warp == AB_CWARPS) {
+  if (warp == AB_W_MMA_S) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
 }
 
 }  // namespace plm
+
+extern "C" int plm_debug_counters(unsigned long long* out, int32_t n, int32_t reset) {
+  if (!out || n <= 0 || n > 32) return plm::fail(PLM_ERR_INVALID, "debug_counters: bad argument");
+  cudaError_t e = cudaMemcpyFromSymbol(out, plm::g_dbg_counters, sizeof(unsigned long long) * n);
+  if (e != cudaSuccess) return plm::fail(PLM_ERR_CUDA, "debug_counters: %s", cudaGetErrorString(e));
+  if (reset) {
+    unsigned long long zeros[32] = {0};
+    e = cudaMemcpyToSymbol(plm::g_dbg_counters, zeros, sizeof(zeros));
+    if (e != cudaSuccess) return plm::fail(PLM_ERR_CUDA, "debug_counters reset: %s", cudaGetErrorString(e));
+  }
+  return PLM_OK;
+}
 
 extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                             const int32_t* seg_start, const float* rope_table, void* dqkv, float* delta,
