@@ -44,27 +44,38 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
-__device__ __forceinline__ void decode_work(const GemmParams& p, int w, int& m_blk, int& n_blk, int& kb0, int& kb1) {
-  const int tiles = p.num_m * p.num_n;
+// Work item -> (m block, n block, k range).  With CL = 2 a work item is a PAIR of M-adjacent tiles processed by the two
+// CTAs of a cluster in lock-step (they share — and multicast — the B tile); `rank` selects the CTA's half of the pair.
+template <int CL>
+__device__ __forceinline__ void decode_work(const GemmParams& p, int w, int rank, int& m_blk, int& n_blk, int& kb0,
+                                            int& kb1) {
+  const int num_mg = (p.num_m + CL - 1) / CL;
+  const int tiles = num_mg * p.num_n;
   const int tile = w % tiles;
   const int split = w / tiles;
+  int mg;
   if (p.n_fastest) {
     n_blk = tile % p.num_n;
-    m_blk = tile / p.num_n;
+    mg = tile / p.num_n;
   } else {
-    m_blk = tile % p.num_m;
-    n_blk = tile / p.num_m;
+    mg = tile % num_mg;
+    n_blk = tile / num_mg;
   }
+  m_blk = mg * CL + rank;
   const int per = (p.kblocks + p.splits - 1) / p.splits;
   kb0 = split * per;
   kb1 = min(p.kblocks, kb0 + per);
 }
 
-template <int BN, bool A_K, bool B_K>
+template <int BN, bool A_K, bool B_K, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
+  static_assert(CL == 1 || CL == 2, "cluster of 1 or 2 CTAs");
+  const int rank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cluster_id = blockIdx.x / CL;
+  const int num_clusters = gridDim.x / CL;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
@@ -78,14 +89,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total = p.num_m * p.num_n * p.splits;
+  const int total = ((p.num_m + CL - 1) / CL) * p.num_n * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);  // CL = 2: the stage is overwritten in BOTH CTAs, so both must have consumed it
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
@@ -99,6 +110,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // the peer's barriers must be initialised before anything can arrive on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -107,9 +119,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      for (int w = cluster_id; w < total; w += num_clusters) {
         int m_blk, n_blk, kb0, kb1;
-        decode_work(p, w, m_blk, n_blk, kb0, kb1);
+        decode_work<CL>(p, w, rank, m_blk, n_blk, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
@@ -122,12 +134,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int g = 0; g < BM / 64; ++g)
               tma_load_2d(a_dst + g * (BK * 128), &tmA, &full[s], m_blk * BM + g * 64, kb * BK);
           }
-          if (B_K) {
-            tma_load_2d(b_dst, &tmB, &full[s], kb * BK, n_blk * BN);
-          } else {
+          if (CL == 1) {
+            if (B_K) {
+              tma_load_2d(b_dst, &tmB, &full[s], kb * BK, n_blk * BN);
+            } else {
 #pragma unroll
-            for (int g = 0; g < BN / 64; ++g)
-              tma_load_2d(b_dst + g * (BK * 128), &tmB, &full[s], n_blk * BN + g * 64, kb * BK);
+              for (int g = 0; g < BN / 64; ++g)
+                tma_load_2d(b_dst + g * (BK * 128), &tmB, &full[s], n_blk * BN + g * 64, kb * BK);
+            }
+          } else {
+            // each CTA fetches HALF of the shared B tile and multicasts it into both CTAs' stage buffers:
+            // L2 -> SM traffic per CTA drops from A + B to A + B/2
+            if (B_K) {
+              tma_load_2d_mc(b_dst + rank * (BN / 2) * 128, &tmB, &full[s], kb * BK, n_blk * BN + rank * (BN / 2), 0x3);
+            } else {
+#pragma unroll
+              for (int g = 0; g < BN / 128; ++g) {
+                const int gg = rank * (BN / 128) + g;
+                tma_load_2d_mc(b_dst + gg * (BK * 128), &tmB, &full[s], n_blk * BN + gg * 64, kb * BK, 0x3);
+              }
+            }
           }
           if (++s == STAGES) {
             s = 0;
@@ -143,9 +169,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+      for (int w = cluster_id; w < total; w += num_clusters, ++it) {
         int m_blk, n_blk, kb0, kb1;
-        decode_work(p, w, m_blk, n_blk, kb0, kb1);
+        decode_work<CL>(p, w, rank, m_blk, n_blk, kb0, kb1);
         const int a = it & 1;
         const uint32_t aph = (it >> 1) & 1;
         mbar_wait(&tempty[a], aph ^ 1);
@@ -164,7 +190,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                        : make_smem_desc_sw128(b_addr + k * 2048, BK * 128, 1024);
             umma_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[s]);
+          if (CL == 2)
+            umma_commit_mc(&empty[s], 0x3);
+          else
+            umma_commit(&empty[s]);
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -177,9 +206,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     int it = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
+    for (int w = cluster_id; w < total; w += num_clusters, ++it) {
       int m_blk, n_blk, kb0, kb1;
-      decode_work(p, w, m_blk, n_blk, kb0, kb1);
+      decode_work<CL>(p, w, rank, m_blk, n_blk, kb0, kb1);
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
       mbar_wait(&tfull[a], aph);
@@ -271,25 +300,40 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
-template <int BN, bool A_K, bool B_K>
+template <int BN, bool A_K, bool B_K, int CL>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_kernel<BN, A_K, B_K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_kernel<BN, A_K, B_K, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return fail(PLM_ERR_CUDA, "gemm smem attribute: %s", cudaGetErrorString(attr_err));
-  const int total = p.num_m * p.num_n * p.splits;
-  const int grid = total < sm_count() ? total : sm_count();
-  gemm_kernel<BN, A_K, B_K><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  const int total = ((p.num_m + CL - 1) / CL) * p.num_n * p.splits;
+  int clusters = sm_count() / CL;
+  if (total < clusters) clusters = total;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_K, B_K, CL>, tmA, tmB, p);
+  if (e != cudaSuccess) return fail(PLM_ERR_CUDA, "gemm_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_kernel");
 }
 
@@ -356,6 +400,12 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
     if (forced == 0 || forced == 1) p.n_fastest = forced;
   }
   p.num_n = static_cast<int>((a->N + bn - 1) / bn);
+  // 2-CTA clusters (M-adjacent tiles sharing a multicast B tile) whenever there is more than one M block
+  int cl = (p.num_m >= 2 && bn == 256) ? 2 : 1;
+  {
+    const int forced = env_int("PLM_GEMM_CLUSTER", 0);
+    if (forced == 1 || (forced == 2 && bn == 256)) cl = forced;
+  }
 
   int splits = a->splits;
   if (a->epilogue != PLM_EPI_ATOMIC_F32) {
@@ -364,7 +414,7 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   } else if (splits <= 0) {
     // Pick the split count that fills whole waves of the persistent grid: efficiency = items / (waves * SMs), with a
     // small penalty per split (each split adds one fp32 red.add pass over the output tile).
-    const int tiles = p.num_m * p.num_n;
+    const int tiles = ((p.num_m + cl - 1) / cl) * p.num_n * cl;
     const int max_splits = p.kblocks / 8 > 0 ? (p.kblocks / 8 < 32 ? p.kblocks / 8 : 32) : 1;  // >= 8 k-blocks each
     double best = -1.0;
     splits = 1;
@@ -393,20 +443,22 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
     rc = make_tmap_bf16_2d(&tmA, a->A, a->K, a->M, a->lda, BK, 64);
   if (rc != PLM_OK) return rc;
   if (b_k)
-    rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, bn, 64);
+    rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, bn / cl, 64);  // cluster: each CTA fetches half the rows
   else
     rc = make_tmap_bf16_2d(&tmB, a->B, a->K, a->N, a->ldb, BK, 64);
   if (rc != PLM_OK) return rc;
 
-#define PLM_DISPATCH(BN_)                                                        \
-  if (a_k && b_k) return launch_gemm<BN_, true, true>(tmA, tmB, p, stream);      \
-  if (a_k && !b_k) return launch_gemm<BN_, true, false>(tmA, tmB, p, stream);    \
-  if (!a_k && b_k) return launch_gemm<BN_, false, true>(tmA, tmB, p, stream);    \
-  return launch_gemm<BN_, false, false>(tmA, tmB, p, stream);
-  if (bn == 256) {
-    PLM_DISPATCH(256)
+#define PLM_DISPATCH(BN_, CL_)                                                        \
+  if (a_k && b_k) return launch_gemm<BN_, true, true, CL_>(tmA, tmB, p, stream);      \
+  if (a_k && !b_k) return launch_gemm<BN_, true, false, CL_>(tmA, tmB, p, stream);    \
+  if (!a_k && b_k) return launch_gemm<BN_, false, true, CL_>(tmA, tmB, p, stream);    \
+  return launch_gemm<BN_, false, false, CL_>(tmA, tmB, p, stream);
+  if (bn == 256 && cl == 2) {
+    PLM_DISPATCH(256, 2)
+  } else if (bn == 256) {
+    PLM_DISPATCH(256, 1)
   } else {
-    PLM_DISPATCH(128)
+    PLM_DISPATCH(128, 1)
   }
 #undef PLM_DISPATCH
 }

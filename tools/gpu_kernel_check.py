@@ -393,17 +393,69 @@ def case_gemm_perf():
     }
     for vname, fn in variants.items():
       rec = {'case': f'{name} {vname} M{M} N{n} K{k}'}
-      for bn in (256, 128):
+      for cl in (1, 2):
         for raster in (0, 1):
-          os.environ['PLM_GEMM_BN'] = str(bn)
+          os.environ['PLM_GEMM_CLUSTER'] = str(cl)
           os.environ['PLM_GEMM_RASTER'] = str(raster)
-          rec[f'bn{bn}_r{raster}'] = round(flops / _time(fn, 6) / 1e9, 0)
-      os.environ.pop('PLM_GEMM_BN')
+          rec[f'cl{cl}_r{raster}'] = round(flops / _time(fn, 6) / 1e9, 0)
+      os.environ.pop('PLM_GEMM_CLUSTER')
       os.environ.pop('PLM_GEMM_RASTER')
       rec['auto'] = round(flops / _time(fn, 6) / 1e9, 0)
       rec['cublas'] = round(flops / _time(cublas[vname], 6) / 1e9, 0)
       out.append(rec)
     del x, w, y, dy, dx, dw
+  return out
+
+
+def case_bw_perf():
+  """Achieved GB/s of the bandwidth kernels at the 420M shapes (algorithmic bytes / CUDA-event time)."""
+  import torch
+  from plainlm_b200 import ops, _lib
+
+  dev = 'cuda'
+  M, d, F, V = 16384, 1024, 2816, 50280
+  bf = torch.bfloat16
+  x = torch.randn(M, d, device=dev)
+  w = torch.ones(d, device=dev)
+  y = torch.empty(M, d, device=dev, dtype=bf)
+  rstd = torch.empty(M, device=dev)
+  dy = torch.randn(M, d, device=dev).to(bf)
+  nb = ops.rmsnorm_bwd_blocks(M)
+  part = torch.empty(nb, d, device=dev)
+  dx = torch.randn(M, d, device=dev)
+  dxb = torch.empty(M, d, device=dev, dtype=bf)
+  dw = torch.zeros(d, device=dev)
+  u = torch.randn(M, 2 * F, device=dev).to(bf)
+  h = torch.empty(M, F, device=dev, dtype=bf)
+  dh = torch.randn(M, F, device=dev).to(bf)
+  du = torch.empty(M, 2 * F, device=dev, dtype=bf)
+  logits = torch.randn(M, V, device=dev).to(bf)
+  tg = torch.randint(0, V, (M,), device=dev)
+  rl, rlse, stats = torch.empty(M, device=dev), torch.empty(M, device=dev), torch.zeros(4, device=dev)
+  n = 411_304_960
+  p = torch.randn(n, device=dev)
+  g = torch.randn(n, device=dev)
+  m = torch.zeros(n, device=dev)
+  v = torch.zeros(n, device=dev)
+  pb = torch.empty(n, device=dev, dtype=bf)
+  ws = torch.empty(_lib.SUMSQ_WORKSPACE, device=dev)
+  gs = torch.zeros(1, device=dev)
+  ops.rmsnorm_fwd(x, w, y, rstd, 1e-6)
+  cases = [
+    ('rmsnorm_fwd', lambda: ops.rmsnorm_fwd(x, w, y, rstd, 1e-6), M * d * 6),
+    ('rmsnorm_bwd', lambda: ops.rmsnorm_bwd(dy, x, w, rstd, dx, dx, dxb, part), M * d * 16),
+    ('colsum_accum', lambda: ops.colsum_accum(part, dw, nb), nb * d * 4),
+    ('swiglu_fwd', lambda: ops.swiglu_fwd(u, h), M * F * 6),
+    ('swiglu_bwd', lambda: ops.swiglu_bwd(dh, u, du), M * F * 10),
+    ('ce_fwd_bwd', lambda: ops.ce_fwd_bwd(logits, tg, rl, rlse, stats, V, 1.0, True), M * V * 6),
+    ('sumsq', lambda: ops.sumsq(g, ws, gs), n * 4),
+    ('adamw', lambda: ops.adamw_step(p, g, m, v, pb, 1e-3, 0.9, 0.95, 1e-8, 0.1, 3, gnorm_sq=gs, max_norm=1.0), n * 30),
+    ('cast_f32_bf16', lambda: ops.cast_f32_bf16(p, pb), n * 6),
+  ]
+  out = []
+  for name, fn, nbytes in cases:
+    ms = _time(fn, 10)
+    out.append({'case': name, 'ms': round(ms, 4), 'GBps': round(nbytes / ms / 1e6, 0), 'frac_of_6544': round(nbytes / ms / 1e6 / 6543.7, 3)})
   return out
 
 
@@ -480,6 +532,7 @@ CASES['attn_bwd_doc_rope'] = lambda: case_attn_bwd(2, 512, 2, doc=True, rope=Tru
 CASES['bandwidth'] = case_bandwidth
 CASES['gemm_perf'] = case_gemm_perf
 CASES['attn_perf'] = case_attn_perf
+CASES['bw_perf'] = case_bw_perf
 
 
 def main():
