@@ -106,36 +106,51 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
         tma_load_2d(sV, &tmQKV, &kv_full[0], 2 * d + h * ATT_HD, kr);
       }
       mbar_wait(q_full, 0);
+      // descriptors are built once; per K-step only the 14-bit start-address field advances (tight issue loop)
+      const uint64_t q_desc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      const uint64_t k_desc0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t v_desc0 = make_smem_desc_sw128(smem_u32(sV), ATT_TILE_BYTES, 1024);  // MN-major view
+      const uint64_t p_desc = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
+      auto issue_s = [&](int st) {
+        const uint64_t k_desc = k_desc0 + st * (ATT_TILE_BYTES >> 4);
+#pragma unroll
+        for (int k = 0; k < ATT_HD / 16; ++k) umma_ss(tS, q_desc + k * 2, k_desc + k * 2, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(s_full);
+      };
+      auto load_kv = [&](int it_next) {
+        const int nst = it_next & 1;
+        const int kr = static_cast<int>(static_cast<int64_t>(b) * T + (j_lo + it_next) * ATT_BK);
+        mbar_arrive_expect_tx(&kv_full[nst], 2 * ATT_TILE_BYTES);
+        tma_load_2d(sK + nst * ATT_TILE_BYTES, &tmQKV, &kv_full[nst], d + h * ATT_HD, kr);
+        tma_load_2d(sV + nst * ATT_TILE_BYTES, &tmQKV, &kv_full[nst], 2 * d + h * ATT_HD, kr);
+      };
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      if (n_it > 1) load_kv(1);
       for (int it = 0; it < n_it; ++it) {
         const int st = it & 1;
-        mbar_wait(&kv_full[st], (it >> 1) & 1);
-        if (it > 0) mbar_wait(s_empty, (it - 1) & 1);
-        tc_fence_after();
-        const uint32_t q_addr = smem_u32(sQ);
-        const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
-        const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
-        const uint32_t p_addr = smem_u32(sP);
-#pragma unroll
-        for (int k = 0; k < ATT_HD / 16; ++k)
-          umma_ss(tS, make_smem_desc_sw128(q_addr + k * 32, 16, 1024), make_smem_desc_sw128(k_addr + k * 32, 16, 1024),
-                  idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(s_full);
-        if (it + 1 < n_it) {  // prefetch next K/V tile
-          const int nst = (it + 1) & 1;
-          mbar_wait(&kv_empty[nst], (((it + 1) >> 1) & 1) ^ 1);
-          const int kr = static_cast<int>(static_cast<int64_t>(b) * T + (j_lo + it + 1) * ATT_BK);
-          mbar_arrive_expect_tx(&kv_full[nst], 2 * ATT_TILE_BYTES);
-          tma_load_2d(sK + nst * ATT_TILE_BYTES, &tmQKV, &kv_full[nst], d + h * ATT_HD, kr);
-          tma_load_2d(sV + nst * ATT_TILE_BYTES, &tmQKV, &kv_full[nst], 2 * d + h * ATT_HD, kr);
+        // S of the NEXT key tile goes out as soon as the softmax warps have read the current one out of tensor memory,
+        // ahead of this tile's P·V: the next softmax never waits for the tensor pipe.
+        if (it + 1 < n_it) {
+          mbar_wait(&kv_full[st ^ 1], ((it + 1) >> 1) & 1);
+          mbar_wait(s_empty, it & 1);
+          tc_fence_after();
+          issue_s(st ^ 1);
         }
         mbar_wait(p_full, it & 1);
         tc_fence_after();
+        const uint64_t v_desc = v_desc0 + st * (ATT_TILE_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < ATT_BK / 16; ++k)
-          umma_ss(tO, make_smem_desc_sw128(p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32, 16, 1024),
-                  make_smem_desc_sw128(v_addr + k * 2048, ATT_TILE_BYTES, 1024), idesc_o, (it > 0 || k > 0) ? 1u : 0u);
+          umma_ss(tO, p_desc + ((k >> 2) * ATT_TILE_BYTES + (k & 3) * 32) / 16, v_desc + k * (2048 >> 4), idesc_o,
+                  (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
         umma_commit(pv_done);
+        if (it + 2 < n_it) {  // refill this K/V stage for tile it+2 once P·V has drained it
+          mbar_wait(&kv_empty[st], (it >> 1) & 1);
+          load_kv(it + 2);
+        }
       }
     }
   } else {

@@ -407,6 +407,49 @@ def case_gemm_perf():
   return out
 
 
+def case_gemm_sustained():
+  """Seconds-long back-to-back runs (power-capped regime): sustained TFLOP/s, SM clock and power, ours vs cuBLASLt."""
+  import subprocess as sp
+  import statistics
+  import torch
+  from plainlm_b200 import ops
+
+  dev = 'cuda'
+  M, n, k = 16384, 5632, 1024
+  x = torch.randn(M, k, device=dev).to(torch.bfloat16)
+  w = torch.randn(n, k, device=dev).to(torch.bfloat16)
+  y = torch.empty(M, n, device=dev, dtype=torch.bfloat16)
+  flops = 2.0 * M * n * k
+  out = []
+  variants = [('ours_cl2', lambda: ops.gemm(x, w, y), {'PLM_GEMM_CLUSTER': '2'}),
+              ('ours_cl1', lambda: ops.gemm(x, w, y), {'PLM_GEMM_CLUSTER': '1'}),
+              ('cublas', lambda: torch.matmul(x, w.t(), out=y), {})]
+  for name, fn, env in variants:
+    os.environ.update(env)
+    for _ in range(20):
+      fn()
+    torch.cuda.synchronize()
+    mon = sp.Popen(['nvidia-smi', '--query-gpu=clocks.sm,power.draw', '--format=csv,noheader,nounits', '-lms', '100'],
+                   stdout=sp.PIPE, text=True)
+    iters = 12000
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+      fn()
+    e1.record()
+    torch.cuda.synchronize()
+    mon.terminate()
+    lines = mon.communicate()[0].strip().splitlines()
+    clk = [float(l.split(',')[0]) for l in lines[3:] if ',' in l]
+    pw = [float(l.split(',')[1]) for l in lines[3:] if ',' in l]
+    ms = e0.elapsed_time(e1) / iters
+    out.append({'case': f'sustained fc1 fwd {name}', 'tflops': round(flops / ms / 1e9, 0), 'secs': round(ms * iters / 1e3, 2),
+                'sm_mhz_median': statistics.median(clk) if clk else None, 'power_w_median': statistics.median(pw) if pw else None})
+    for kk in env:
+      os.environ.pop(kk)
+  return out
+
+
 def case_bw_perf():
   """Achieved GB/s of the bandwidth kernels at the 420M shapes (algorithmic bytes / CUDA-event time)."""
   import torch
@@ -533,6 +576,7 @@ CASES['bandwidth'] = case_bandwidth
 CASES['gemm_perf'] = case_gemm_perf
 CASES['attn_perf'] = case_attn_perf
 CASES['bw_perf'] = case_bw_perf
+CASES['gemm_sustained'] = case_gemm_sustained
 
 
 def main():
