@@ -9,7 +9,7 @@
 namespace plm {
 
 constexpr int NORM_WARPS = 8;
-constexpr int NORM_BWD_MAX_BLOCKS = 592;  // 4 per SM x 8 warps: enough loads in flight to saturate HBM
+constexpr int NORM_BWD_MAX_BLOCKS = 296;  // 2 per SM x 8 warps resident; each warp prefetches its next row into L2
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -48,6 +48,9 @@ rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __n
   }
 }
 
+// Backward.  A warp owns TWO half-rows at a time?  No: one row per warp, but the row is streamed in two register-light
+// passes — pass 1 (dot product) keeps only packed dy (bf16) and x in registers, pass 2 recomputes from them.  dw partials
+// live in shared memory (one fp32 per column per warp-slot), not registers, which is what lets 4 blocks stay resident.
 template <int VPL>
 __global__ void __launch_bounds__(NORM_WARPS * 32, (VPL <= 8) ? 2 : 1)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
@@ -66,15 +69,30 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
     const float4* xr = reinterpret_cast<const float4*>(x + row * D);
     const uint2* dyr = reinterpret_cast<const uint2*>(dy + row * D);
     const float r = rstd[row];
-    // only the raw row (x fp32, dy bf16) stays in registers; w is re-read from L1 (keeps 2 blocks resident per SM)
     float4 xv[VPL];
     uint2 dv[VPL];
-    float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       xv[i] = __ldcs(xr + i * 32 + lane);
       dv[i] = __ldcs(dyr + i * 32 + lane);
     }
+    {  // pull the NEXT row of this warp into L2 while this one is reduced: the kernel is latency-bound, not bandwidth-bound
+      const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * NORM_WARPS;
+      if (nrow < rows) {
+#pragma unroll
+        for (int i = 0; i < VPL; i += 2)  // one prefetch per lane covers 16 B; lanes 0..31 cover 512 B = 4 lines
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(x + nrow * D + (i * 32 + lane) * 4));
+#pragma unroll
+        for (int i = 0; i < VPL; i += 4)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(dy + nrow * D + (i * 32 + lane) * 4));
+        if (dx_in) {
+#pragma unroll
+          for (int i = 0; i < VPL; i += 2)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(dx_in + nrow * D + (i * 32 + lane) * 4));
+        }
+      }
+    }
+    float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const float4 ww = __ldg(wr + i * 32 + lane);
@@ -83,6 +101,7 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
     }
     dot = warp_sum(dot) * r * (1.0f / D);  // mean_j (dy_j w_j xhat_j)
     float4* dxo = reinterpret_cast<float4*>(dx_out + row * D);
+    const float4* dxi = reinterpret_cast<const float4*>(dx_in ? dx_in + row * D : nullptr);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const float4 ww = __ldg(wr + i * 32 + lane);
@@ -98,13 +117,13 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
       o.z = r * (d2 * ww.z - h2 * dot);
       o.w = r * (d3 * ww.w - h3 * dot);
       if (dx_in) {
-        const float4 a = __ldcs(reinterpret_cast<const float4*>(dx_in + row * D) + i * 32 + lane);
+        const float4 a = __ldcs(dxi + i * 32 + lane);
         o.x += a.x;
         o.y += a.y;
         o.z += a.z;
         o.w += a.w;
       }
-      dxo[i * 32 + lane] = o;
+      __stcs(dxo + i * 32 + lane, o);
       if (dx_bf16) {
         uint2 b;
         b.x = pack_bf16x2(o.x, o.y);
