@@ -264,6 +264,7 @@ def run_ours(args):
   # ---------------------------------------------------------------- one instrumented step: per-kernel CUDA events
   prof = ops.Profiler()
   ops.set_profiler(prof)
+  engine.use_cuda_graphs = False  # per-kernel events need eager launches
   for m in range(accum):
     dev_step(m)
   summ = prof.summary()

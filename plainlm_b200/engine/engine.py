@@ -67,6 +67,7 @@ class TorchEngine(torch.nn.Module):
     self.grad_clip = cfg.grad_clip
     self.dtype = cfg.dtype
     self.intra_doc_masking = getattr(cfg, 'intra_doc_masking', False)
+    self.use_cuda_graphs = getattr(cfg, 'cuda_graphs', True)  # optional key: replay the micro-step from a CUDA graph
     self.device = device
     if 'cuda' not in str(device):
       raise RuntimeError('plainlm_b200.TorchEngine needs a CUDA device (B200); there is no CPU path')
@@ -164,8 +165,12 @@ class TorchEngine(torch.nn.Module):
     last = self.accumulated_samples == self.accumulation_steps
     on_bucket = self.reducer.bucket_ready if (self.reducer is not None and last) else None
 
-    loss_val = self.rt.loss_and_backward(inputs, targets, seg_start, grad_scale=1.0 / self.accumulation_steps,
-                                         backward=True, on_bucket=on_bucket)
+    if self.use_cuda_graphs and on_bucket is None:
+      loss_val = self.rt.graphed_loss_and_backward(inputs, targets, seg_start,
+                                                   grad_scale=1.0 / self.accumulation_steps)
+    else:  # the data-parallel micro-step interleaves NCCL buckets with backward: launched eagerly
+      loss_val = self.rt.loss_and_backward(inputs, targets, seg_start, grad_scale=1.0 / self.accumulation_steps,
+                                           backward=True, on_bucket=on_bucket)
     self._record_loss(loss_val)
 
     if last:

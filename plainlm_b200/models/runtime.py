@@ -139,6 +139,11 @@ class _Workspace:
     self.dq_acc = e(M, d, dtype=f32)
     self.nblk = ops.rmsnorm_bwd_blocks(M)
     self.dw_part = e(self.nblk, d, dtype=f32)
+    # static inputs + captured CUDA graphs of the micro-step (keyed by (masked, grad_scale))
+    self.ids = torch.zeros(B, T, device=dev, dtype=torch.int64)
+    self.targets = torch.zeros(B, T, device=dev, dtype=torch.int64)
+    self.seg = torch.zeros(B * T, device=dev, dtype=torch.int32)
+    self.graphs = {}
 
 
 class TrainRuntime:
@@ -211,6 +216,50 @@ class TrainRuntime:
     if backward:
       self.backward_from_dlogits(ids, seg_start, ws, on_bucket)
     return loss
+
+  def graphed_loss_and_backward(self, ids, targets, seg_start=None, grad_scale=1.0):
+    """Same work as loss_and_backward(backward=True, on_bucket=None), replayed from a CUDA graph: the ~590 launches of
+    a micro-step are captured once per (shape, masked, grad_scale) and then cost one cudaGraphLaunch — no per-kernel
+    host work, no launch gaps.  Inputs are copied into static device buffers (stream-ordered, so the previous replay
+    has finished reading them)."""
+    self.flat.refresh_if_stale()
+    B, T = ids.shape
+    ws = self.workspace(B, T)
+    ws.ids.copy_(ids, non_blocking=True)
+    ws.targets.copy_(targets, non_blocking=True)
+    masked = seg_start is not None
+    if masked:
+      ws.seg.copy_(seg_start.reshape(-1), non_blocking=True)
+    key = (masked, float(grad_scale))
+    rec = ws.graphs.get(key)
+    if rec is None:
+      seg = ws.seg if masked else None
+      cur = torch.cuda.current_stream()
+      side = torch.cuda.Stream()
+      side.wait_stream(cur)
+      with torch.cuda.stream(side):
+        saved = self.flat.grads.clone()  # the warm-up / capture runs must not leak into the accumulated gradients
+        self._micro_step(ws, seg, grad_scale)  # warm-up: lazy one-time initialisation happens outside the capture
+        graph = torch.cuda.CUDAGraph()
+        n0 = ops.LAUNCHES
+        with torch.cuda.graph(graph, stream=side):
+          self._micro_step(ws, seg, grad_scale)
+        launches = ops.LAUNCHES - n0
+        self.flat.grads.copy_(saved)
+        del saved
+      cur.wait_stream(side)
+      rec = (graph, launches)
+      ws.graphs[key] = rec
+    graph, launches = rec
+    graph.replay()
+    ops.LAUNCHES += launches
+    return ws.stats[2].clone()
+
+  def _micro_step(self, ws, seg, grad_scale):
+    self.forward_logits(ws.ids, seg, ws)
+    ops.ce_fwd_bwd(ws.logits, ws.targets.reshape(-1), ws.row_loss, ws.row_lse, ws.stats, self.model.vocab_size,
+                   grad_scale=grad_scale, write_grad=True)
+    self.backward_from_dlogits(ws.ids, seg, ws, None)
 
   def _wgrad(self, dy, x, name):
     """grad[name] += dy^T x  (contraction over tokens, both operands read in place as MN-major)."""
