@@ -129,7 +129,7 @@ class _Workspace:
     self.stats = torch.zeros(4, device=dev, dtype=f32)
     # backward temporaries
     self.dx = e(M, d, dtype=f32)
-    self.dx_b = e(M, d)
+    self.dx_b2 = [e(M, d), e(M, d)]  # ping-pong: the side-stream wgrad of one branch reads it while the next is written
     self.dh = e(M, d)
     self.dg = e(M, F)
     self.du = e(M, 2 * F)
@@ -161,6 +161,8 @@ class TrainRuntime:
     gr = lambda n: p[n].grad  # noqa: E731
     self.names = p
     self.tied = model.lm_head.weight is model.embed_tokens.weight
+    self.wstream = torch.cuda.Stream(device=device)  # weight-gradient GEMMs run here, filling the tails of the main stream
+    self._readers = {}
     self.W = {n: sh(n) for n in p}   # bf16 GEMM operands
     self.G = {n: gr(n) for n in p}   # fp32 grad views
     self.P = {n: p[n].data for n in p}
@@ -261,9 +263,25 @@ class TrainRuntime:
                    grad_scale=grad_scale, write_grad=True)
     self.backward_from_dlogits(ws.ids, seg, ws, None)
 
-  def _wgrad(self, dy, x, name):
-    """grad[name] += dy^T x  (contraction over tokens, both operands read in place as MN-major)."""
-    ops.gemm(dy, x, self.G[name], a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ATOMIC_F32, splits=0)
+  def _wgrad(self, dy, x, name, guard):
+    """grad[name] += dy^T x  (contraction over tokens, both operands read in place as MN-major), on the side stream:
+    nothing downstream in backward needs it, so it overlaps the main stream and fills the idle SMs of its kernel tails.
+    `guard` names the dy buffer: whoever overwrites it later first waits for this GEMM (_release)."""
+    main = torch.cuda.current_stream()
+    ready = torch.cuda.Event()
+    ready.record(main)
+    self.wstream.wait_event(ready)
+    with torch.cuda.stream(self.wstream):
+      ops.gemm(dy, x, self.G[name], a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ATOMIC_F32, splits=0)
+      done = torch.cuda.Event()
+      done.record(self.wstream)
+    self._readers[guard] = done
+
+  def _release(self, guard):
+    """Make the current stream wait until the side-stream GEMM that reads buffer `guard` has finished."""
+    ev = self._readers.pop(guard, None)
+    if ev is not None:
+      torch.cuda.current_stream().wait_event(ev)
 
   def _dgrad(self, dy, name, out):
     """out = dy W[name]  (W read in place as an MN-major B operand)."""
@@ -274,40 +292,59 @@ class TrainRuntime:
     B, T, H, hd, L = ws.B, ws.T, m.n_heads, m.head_dim, self.L
     P, G = self.P, self.G
     bucket = 0
+    flip = 0
 
-    def done():
+    def done(on_side=False):
       nonlocal bucket
       if on_bucket is not None:
-        on_bucket(bucket)
+        if on_side:  # the bucket is final when the side-stream wgrads are: let the reducer record its event there
+          with torch.cuda.stream(self.wstream):
+            on_bucket(bucket)
+        else:
+          on_bucket(bucket)
       bucket += 1
+
+    def next_dxb():
+      nonlocal flip
+      flip ^= 1
+      self._release(f'dx_b{flip}')
+      return ws.dx_b2[flip]
 
     dlogits = ws.logits  # overwritten in place by the CE kernel
     self._dgrad(dlogits, 'lm_head.weight', ws.dh)
-    self._wgrad(dlogits, ws.hf, 'lm_head.weight')
+    self._wgrad(dlogits, ws.hf, 'lm_head.weight', 'logits')
     if not self.tied:
-      done()
-    ops.rmsnorm_bwd(ws.dh, ws.x[L], P['out_norm.weight'], ws.rstd_f, None, ws.dx, ws.dx_b, ws.dw_part)
+      done(on_side=True)
+    dx_b = next_dxb()
+    ops.rmsnorm_bwd(ws.dh, ws.x[L], P['out_norm.weight'], ws.rstd_f, None, ws.dx, dx_b, ws.dw_part)
     ops.colsum_accum(ws.dw_part, G['out_norm.weight'], ws.nblk)
     for l in reversed(range(L)):
       pre = f'layers.{l}.'
       # ---- MLP branch: x[l+1] = x_mid + fc2(silu(a) * z)
-      self._dgrad(ws.dx_b, pre + 'mlp.fc2.weight', ws.dg)
-      self._wgrad(ws.dx_b, ws.g[l], pre + 'mlp.fc2.weight')
+      self._dgrad(dx_b, pre + 'mlp.fc2.weight', ws.dg)
+      self._wgrad(dx_b, ws.g[l], pre + 'mlp.fc2.weight', f'dx_b{flip}')
+      self._release('du')
       ops.swiglu_bwd(ws.dg, ws.u[l], ws.du)
       self._dgrad(ws.du, pre + 'mlp.fc1.weight', ws.dh)
-      self._wgrad(ws.du, ws.h2[l], pre + 'mlp.fc1.weight')
-      ops.rmsnorm_bwd(ws.dh, ws.x_mid[l], P[pre + 'mlp_norm.weight'], ws.rstd2[l], ws.dx, ws.dx, ws.dx_b, ws.dw_part)
+      self._wgrad(ws.du, ws.h2[l], pre + 'mlp.fc1.weight', 'du')
+      dx_b = next_dxb()
+      ops.rmsnorm_bwd(ws.dh, ws.x_mid[l], P[pre + 'mlp_norm.weight'], ws.rstd2[l], ws.dx, ws.dx, dx_b, ws.dw_part)
       ops.colsum_accum(ws.dw_part, G[pre + 'mlp_norm.weight'], ws.nblk)
       # ---- attention branch: x_mid = x[l] + w_out(attn(rope(w_qkv(h1))))
-      self._dgrad(ws.dx_b, pre + 'attn.w_out.weight', ws.dattn)
-      self._wgrad(ws.dx_b, ws.attn[l], pre + 'attn.w_out.weight')
+      self._dgrad(dx_b, pre + 'attn.w_out.weight', ws.dattn)
+      self._wgrad(dx_b, ws.attn[l], pre + 'attn.w_out.weight', f'dx_b{flip}')
+      self._release('dqkv')
       ops.attn_bwd(ws.qkv[l], ws.attn[l], ws.dattn, ws.lse[l], ws.dqkv, ws.delta, ws.dq_acc, B, T, H, hd,
                    seg_start=seg_start, rope_table=self.rope)
       self._dgrad(ws.dqkv, pre + 'attn.w_qkv.weight', ws.dh)
-      self._wgrad(ws.dqkv, ws.h1[l], pre + 'attn.w_qkv.weight')
-      done()
-      ops.rmsnorm_bwd(ws.dh, ws.x[l], P[pre + 'attn_norm.weight'], ws.rstd1[l], ws.dx, ws.dx, ws.dx_b, ws.dw_part)
+      self._wgrad(ws.dqkv, ws.h1[l], pre + 'attn.w_qkv.weight', 'dqkv')
+      done(on_side=True)
+      dx_b = next_dxb()
+      ops.rmsnorm_bwd(ws.dh, ws.x[l], P[pre + 'attn_norm.weight'], ws.rstd1[l], ws.dx, ws.dx, dx_b, ws.dw_part)
       ops.colsum_accum(ws.dw_part, G[pre + 'attn_norm.weight'], ws.nblk)
+    # join: every side-stream GEMM is complete before anything after backward (next forward, reducer, optimizer)
+    for guard in list(self._readers):
+      self._release(guard)
     ops.embed_bwd(ids.reshape(-1), ws.dx, G['embed_tokens.weight'])
     done()  # embedding bucket
     done()  # norm-weight bucket
