@@ -120,6 +120,11 @@ int plm_rmsnorm_bwd(const void* dy_bf16, const float* x, const float* w, const f
                     plm_stream_t stream);
 /* dw[d] += sum over blocks of dw_partial (deterministic order). */
 int plm_colsum_accum(const float* partial, float* dw, int32_t nblocks, int32_t d, plm_stream_t stream);
+/* `batch` such reductions in one launch: partial [batch][nblocks][d] -> dw [batch][d] (both contiguous).  The runtime
+ * keeps the partials of all 2L+1 norms and folds them once per micro-step (their gradients are contiguous in the flat
+ * gradient buffer, in backward order). */
+int plm_colsum_accum_batched(const float* partial, float* dw, int32_t nblocks, int32_t d, int32_t batch,
+                             plm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------ SwiGLU
  * models/components.py:55-56: u = [a | z] (bf16 [rows, 2F]); h = silu(a) * z (bf16 [rows, F]). */

@@ -42,6 +42,7 @@ SIGNATURES = {
   'plm_rmsnorm_bwd_blocks': (c_int32, [_I64]),
   'plm_rmsnorm_bwd': (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
   'plm_colsum_accum': (c_int32, [_P, _P, _I32, _I32, _P]),
+  'plm_colsum_accum_batched': (c_int32, [_P, _P, _I32, _I32, _I32, _P]),
   'plm_swiglu_fwd': (c_int32, [_P, _P, _I64, _I32, _P]),
   'plm_swiglu_bwd': (c_int32, [_P, _P, _P, _I64, _I32, _P]),
   'plm_embed_fwd': (c_int32, [_P, _P, _P, _I64, _I32, _I64, _P]),

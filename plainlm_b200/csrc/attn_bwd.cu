@@ -111,23 +111,27 @@ dq_finalize_kernel(const float* __restrict__ dq_acc, const float* __restrict__ t
 template <bool MASK>
 __device__ __forceinline__ void bwd_p_chunk(const uint32_t (&t)[32], float (&p)[32], const float* lse2, const int32_t* sg,
                                             int kj, int qpos0, float scale_log2) {
+  const float2 sc2 = make_float2(scale_log2, scale_log2);
 #pragma unroll
   for (int q4 = 0; q4 < 8; ++q4) {
     const float4 l = *reinterpret_cast<const float4*>(lse2 + q4 * 4);
-    const float lv[4] = {l.x, l.y, l.z, l.w};
-    int4 g = make_int4(0, 0, 0, 0);
-    if (MASK) g = *reinterpret_cast<const int4*>(sg + q4 * 4);
-    const int gv[4] = {g.x, g.y, g.z, g.w};
+    // packed fp32x2 FMA (sm_100): two exp2 arguments per instruction
+    const float2 a0 = __ffma2_rn(make_float2(__uint_as_float(t[4 * q4 + 0]), __uint_as_float(t[4 * q4 + 1])), sc2,
+                                 make_float2(-l.x, -l.y));
+    const float2 a1 = __ffma2_rn(make_float2(__uint_as_float(t[4 * q4 + 2]), __uint_as_float(t[4 * q4 + 3])), sc2,
+                                 make_float2(-l.z, -l.w));
+    float v[4] = {ex2b(a0.x), ex2b(a0.y), ex2b(a1.x), ex2b(a1.y)};
+    if (MASK) {
+      const int4 g = *reinterpret_cast<const int4*>(sg + q4 * 4);
+      const int gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int q = q4 * 4 + e;
-      float v = ex2b(fmaf(__uint_as_float(t[q]), scale_log2, -lv[e]));
-      if (MASK) {
-        const int qi = qpos0 + q;
-        if (kj > qi || kj < gv[e]) v = 0.f;
+      for (int e = 0; e < 4; ++e) {
+        const int qi = qpos0 + q4 * 4 + e;
+        if (kj > qi || kj < gv[e]) v[e] = 0.f;
       }
-      p[q] = v;
     }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) p[4 * q4 + e] = v[e];
   }
 }
 
@@ -378,10 +382,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
         const float4 dv = *reinterpret_cast<const float4*>(dl + q4 * 4);
-        p[4 * q4 + 0] *= __uint_as_float(tdp[4 * q4 + 0]) - dv.x;
-        p[4 * q4 + 1] *= __uint_as_float(tdp[4 * q4 + 1]) - dv.y;
-        p[4 * q4 + 2] *= __uint_as_float(tdp[4 * q4 + 2]) - dv.z;
-        p[4 * q4 + 3] *= __uint_as_float(tdp[4 * q4 + 3]) - dv.w;
+        const float2 d0 = __fadd2_rn(make_float2(__uint_as_float(tdp[4 * q4 + 0]), __uint_as_float(tdp[4 * q4 + 1])),
+                                     make_float2(-dv.x, -dv.y));
+        const float2 d1 = __fadd2_rn(make_float2(__uint_as_float(tdp[4 * q4 + 2]), __uint_as_float(tdp[4 * q4 + 3])),
+                                     make_float2(-dv.z, -dv.w));
+        const float2 r0 = __fmul2_rn(make_float2(p[4 * q4 + 0], p[4 * q4 + 1]), d0);
+        const float2 r1 = __fmul2_rn(make_float2(p[4 * q4 + 2], p[4 * q4 + 3]), d1);
+        p[4 * q4 + 0] = r0.x;
+        p[4 * q4 + 1] = r0.y;
+        p[4 * q4 + 2] = r1.x;
+        p[4 * q4 + 3] = r1.y;
       }
       // the previous step's dV MMAs must be done with the P^T columns, its dK/dQ MMAs with the dS^T buffer
       if (it > 0) {

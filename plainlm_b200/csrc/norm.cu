@@ -157,6 +157,9 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
 // dw[c] += sum_b partial[b, c].  Block = 32 columns x 8 row groups; fixed summation order => deterministic.
 __global__ void __launch_bounds__(256)
 colsum_accum_kernel(const float* __restrict__ partial, float* __restrict__ dw, int nblocks, int d) {
+  // blockIdx.y selects one of `batch` independent reductions laid out back to back ([batch][nblocks][d] -> [batch][d])
+  partial += static_cast<int64_t>(blockIdx.y) * nblocks * d;
+  dw += static_cast<int64_t>(blockIdx.y) * d;
   __shared__ float red[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + tx;
@@ -239,6 +242,16 @@ int plm_rmsnorm_bwd(const void* dy_bf16, const float* x, const float* w, const f
                               static_cast<const __nv_bfloat16*>(dy_bf16), x, w, rstd, dx_in, dx_out,
                               static_cast<__nv_bfloat16*>(dx_out_bf16), dw_partial, rows)));
   return check_launch("rmsnorm_bwd");
+}
+
+int plm_colsum_accum_batched(const float* partial, float* dw, int32_t nblocks, int32_t d, int32_t batch,
+                             plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(partial);
+  PLM_REQUIRE(partial && dw && nblocks > 0 && d > 0 && batch > 0 && batch <= 65535, "colsum_accum_batched: bad argument");
+  colsum_accum_kernel<<<dim3((d + 31) / 32, batch), 256, 0, stream>>>(partial, dw, nblocks, d);
+  return check_launch("colsum_accum_batched");
 }
 
 int plm_colsum_accum(const float* partial, float* dw, int32_t nblocks, int32_t d, plm_stream_t stream_) {

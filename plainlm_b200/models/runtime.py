@@ -138,7 +138,7 @@ class _Workspace:
     self.delta = e(B, H, T, dtype=f32)
     self.dq_acc = e(M, d, dtype=f32)
     self.nblk = ops.rmsnorm_bwd_blocks(M)
-    self.dw_part = e(self.nblk, d, dtype=f32)
+    self.dw_part = e(2 * L + 1, self.nblk, d, dtype=f32)  # per-norm partials, folded once per micro-step
     # static inputs + captured CUDA graphs of the micro-step (keyed by (masked, grad_scale))
     self.ids = torch.zeros(B, T, device=dev, dtype=torch.int64)
     self.targets = torch.zeros(B, T, device=dev, dtype=torch.int64)
@@ -161,6 +161,8 @@ class TrainRuntime:
     gr = lambda n: p[n].grad  # noqa: E731
     self.names = p
     self.tied = model.lm_head.weight is model.embed_tokens.weight
+    ns = self.flat.norm_start
+    self.norm_grads = self.flat.grads[ns : ns + (2 * L + 1) * model.dim]
     self.wstream = torch.cuda.Stream(device=device)  # weight-gradient GEMMs run here, filling the tails of the main stream
     self._readers = {}
     self.W = {n: sh(n) for n in p}   # bf16 GEMM operands
@@ -316,8 +318,8 @@ class TrainRuntime:
     if not self.tied:
       done(on_side=True)
     dx_b = next_dxb()
-    ops.rmsnorm_bwd(ws.dh, ws.x[L], P['out_norm.weight'], ws.rstd_f, None, ws.dx, dx_b, ws.dw_part)
-    ops.colsum_accum(ws.dw_part, G['out_norm.weight'], ws.nblk)
+    norm_i = 0  # norms are visited in the order their gradients sit in the flat buffer's last bucket
+    ops.rmsnorm_bwd(ws.dh, ws.x[L], P['out_norm.weight'], ws.rstd_f, None, ws.dx, dx_b, ws.dw_part[norm_i])
     for l in reversed(range(L)):
       pre = f'layers.{l}.'
       # ---- MLP branch: x[l+1] = x_mid + fc2(silu(a) * z)
@@ -328,8 +330,9 @@ class TrainRuntime:
       self._dgrad(ws.du, pre + 'mlp.fc1.weight', ws.dh)
       self._wgrad(ws.du, ws.h2[l], pre + 'mlp.fc1.weight', 'du')
       dx_b = next_dxb()
-      ops.rmsnorm_bwd(ws.dh, ws.x_mid[l], P[pre + 'mlp_norm.weight'], ws.rstd2[l], ws.dx, ws.dx, dx_b, ws.dw_part)
-      ops.colsum_accum(ws.dw_part, G[pre + 'mlp_norm.weight'], ws.nblk)
+      norm_i += 1
+      ops.rmsnorm_bwd(ws.dh, ws.x_mid[l], P[pre + 'mlp_norm.weight'], ws.rstd2[l], ws.dx, ws.dx, dx_b,
+                      ws.dw_part[norm_i])
       # ---- attention branch: x_mid = x[l] + w_out(attn(rope(w_qkv(h1))))
       self._dgrad(dx_b, pre + 'attn.w_out.weight', ws.dattn)
       self._wgrad(dx_b, ws.attn[l], pre + 'attn.w_out.weight', f'dx_b{flip}')
@@ -340,11 +343,13 @@ class TrainRuntime:
       self._wgrad(ws.dqkv, ws.h1[l], pre + 'attn.w_qkv.weight', 'dqkv')
       done(on_side=True)
       dx_b = next_dxb()
-      ops.rmsnorm_bwd(ws.dh, ws.x[l], P[pre + 'attn_norm.weight'], ws.rstd1[l], ws.dx, ws.dx, dx_b, ws.dw_part)
-      ops.colsum_accum(ws.dw_part, G[pre + 'attn_norm.weight'], ws.nblk)
+      norm_i += 1
+      ops.rmsnorm_bwd(ws.dh, ws.x[l], P[pre + 'attn_norm.weight'], ws.rstd1[l], ws.dx, ws.dx, dx_b, ws.dw_part[norm_i])
     # join: every side-stream GEMM is complete before anything after backward (next forward, reducer, optimizer)
     for guard in list(self._readers):
       self._release(guard)
     ops.embed_bwd(ids.reshape(-1), ws.dx, G['embed_tokens.weight'])
     done()  # embedding bucket
+    # all 2L+1 norm-weight gradients in one launch: their slots are contiguous (stride d) in the last flat bucket
+    ops.colsum_accum_batched(ws.dw_part, self.norm_grads, ws.nblk, m.dim, 2 * L + 1)
     done()  # norm-weight bucket

@@ -122,6 +122,13 @@ def colsum_accum(partial, dw, nblocks):
   return dw
 
 
+def colsum_accum_batched(partial, dw, nblocks, d, batch):
+  lib = _lib.load()
+  check(lib.plm_colsum_accum_batched(_ptr(partial, f32, 'partial'), _ptr(dw, f32, 'dw'), nblocks, d, batch, _stream()),
+        'plm_colsum_accum_batched')
+  return dw
+
+
 # ---------------------------------------------------------------------------------------------- SwiGLU
 def swiglu_fwd(u, h):
   lib = _lib.load()
@@ -219,7 +226,7 @@ def seg_start_from_lengths(lengths, offsets, seg_start, B, T):
 # Launch accounting and optional per-call CUDA-event timing, used by bench.py (roofline of the dominant kernel,
 # `gpu_launches`).  Counting is always on (an integer add per call); event timing only when a Profiler is installed.
 KERNELS_PER_CALL = {
-  'gemm': 1, 'attn_fwd': 1, 'attn_bwd': 3, 'rope_qk_': 1, 'rmsnorm_fwd': 1, 'rmsnorm_bwd': 1, 'colsum_accum': 1,
+  'gemm': 1, 'attn_fwd': 1, 'attn_bwd': 3, 'rope_qk_': 1, 'rmsnorm_fwd': 1, 'rmsnorm_bwd': 1, 'colsum_accum': 1, 'colsum_accum_batched': 1,
   'swiglu_fwd': 1, 'swiglu_bwd': 1, 'embed_fwd': 1, 'embed_bwd': 1, 'ce_fwd_bwd': 3, 'sumsq': 2, 'adamw_step': 1,
   'signsgd_step': 1, 'cast_f32_bf16': 1, 'cast_bf16_f32': 1, 'seg_start_from_lengths': 1,
 }  # fmt: skip
