@@ -26,6 +26,10 @@ int ensure_context(const void* device_ptr);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
 
+// Same for an fp32 tensor (box_cols * 4 bytes must be 128).
+int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
+                     uint32_t box_cols);
+
 #define PLM_ENSURE_CONTEXT(ptr)                            \
   do {                                                    \
     if ((ptr) != nullptr) {                               \

@@ -1,10 +1,11 @@
 // tcgen05 GEMM for every nn.Linear of the plainLM train step (models/transformer.py:42,67,114;
 // models/components.py:55-56) — forward, dgrad and wgrad — replacing the cuBLASLt calls PyTorch makes under autocast.
 //
-// One persistent CTA per SM, 192 threads:
+// One persistent CTA per SM, 320 threads:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled boxes, STAGES-deep mbarrier ring)
 //   warp 1      MMA issuer     (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM; owns TMEM alloc/dealloc)
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b, one accumulator row per thread, fused epilogues, direct stores)
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b, one accumulator row per thread, two warps per TMEM lane quarter each
+//               draining half of the columns; fused epilogues with their global operands prefetched; direct stores)
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of
 // tile i+1.  Tile = 128 x BN x 64 with BN in {128, 256}.  Operands may be K-major or MN-major (UMMA descriptor +
 // instruction-descriptor major bits), which is what lets dgrad and wgrad read activations/weights in place.
@@ -16,9 +17,15 @@
 
 namespace plm {
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 4;   // one per TMEM lane quarter
+constexpr int EPI_BUF_BYTES = 128 * 128;  // staging tile: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
+constexpr int GEMM_THREADS = (2 + GEMM_EPI_WARPS) * 32;
 
 struct GemmParams {
   void* C;
@@ -30,6 +37,7 @@ struct GemmParams {
   int splits;
   int rope_cols, rope_T, head_dim;
   int num_m, num_n, kblocks;
+  int debug;      // diagnostics only (PLM_GEMM_DEBUG): 1 = skip epilogue operand loads, 2 = skip stores
   int n_fastest;  // tile rasterisation: 0 = consecutive tiles walk M (B tile reused), 1 = walk N (A tile reused)
 };
 
@@ -41,7 +49,7 @@ struct GemmCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * EPI_BUF_BYTES + BAR_BYTES + 1024;  // + alignment slack
 };
 
 // Work item -> (m block, n block, k range).  With CL = 2 a work item is a PAIR of M-adjacent tiles processed by the two
@@ -69,7 +77,8 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int rank
 
 template <int BN, bool A_K, bool B_K, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   static_assert(CL == 1 || CL == 2, "cluster of 1 or 2 CTAs");
@@ -81,7 +90,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* smem = smem_raw + ((1024 - (smem_u32(smem_raw) & 1023)) & 1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;  // 2 staging tiles for the TMA-store epilogue
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + 2 * EPI_BUF_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
@@ -94,13 +104,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], CL);  // CL = 2: the stage is overwritten in BOTH CTAs, so both must have consumed it
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);
+      mbar_init(&tempty[a], GEMM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -204,98 +215,184 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // TMEM -> registers (one accumulator row per thread) -> fused math -> 128B-swizzled smem staging tile ->
+    // ONE TMA store (or fp32 reduce-add) per 128-byte-wide column chunk.  Register<->global accesses with the
+    // row-per-lane layout touch 32 cache lines per warp instruction and made the epilogue longer than the main loop,
+    // so nothing here uses them: outputs leave through TMA, and the operands that come from global memory (fp32
+    // residual rows, RoPE (cos,sin) rows) are fetched with a coalesced layout (8 lanes per 128-byte row segment, one
+    // sub-chunk ahead) and transposed to row-per-lane through the staging tile.
+    const int q = warp & 3;                    // TMEM lane quarter this warp may read
+    const int r_tile = q * 32 + lane;          // row within the tile
+    const bool elected = (threadIdx.x == 64);  // warp 2, lane 0 issues the bulk stores
+    const bool out_bf16 = (p.epilogue == PLM_EPI_BF16 || p.epilogue == PLM_EPI_BF16_ROPE);
+    const bool is_rope = (p.epilogue == PLM_EPI_BF16_ROPE) && !(p.debug & 1);
+    const bool is_resid = (p.epilogue == PLM_EPI_RESID_F32) && !(p.debug & 1);
+    const int piece = lane & 7;                // coalesced layout: 16-byte piece of a row's 128-byte segment
+    const int lrow0 = q * 32 + (lane >> 3);    // ... of rows lrow0 + 4j, j = 0..7
+    const uint32_t own_off = r_tile * 128;
+    const int own_sw = r_tile & 7;
     int it = 0;
+    uint32_t chunk_no = 0;
     for (int w = cluster_id; w < total; w += num_clusters, ++it) {
       int m_blk, n_blk, kb0, kb1;
       decode_work<CL>(p, w, rank, m_blk, n_blk, kb0, kb1);
       const int a = it & 1;
       const uint32_t aph = (it >> 1) & 1;
-      mbar_wait(&tfull[a], aph);
-      tc_fence_after();
-      const int64_t row = static_cast<int64_t>(m_blk) * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int64_t col0 = static_cast<int64_t>(n_blk) * BN + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(t_row + c * 32, r);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        const int ncols = (p.N - col0) < 32 ? static_cast<int>(p.N - col0) : 32;  // multiple of 8
-        if (p.epilogue == PLM_EPI_BF16 || p.epilogue == PLM_EPI_BF16_ROPE) {
-          if (p.epilogue == PLM_EPI_BF16_ROPE && col0 < p.rope_cols) {
-            const int pos = static_cast<int>(row % p.rope_T);
-            const int pair0 = static_cast<int>(col0 % p.head_dim) >> 1;
-            const float4* tab = reinterpret_cast<const float4*>(
-                p.rope + (static_cast<int64_t>(pos) * (p.head_dim >> 1) + pair0) * 2);
+      const int64_t row_base = static_cast<int64_t>(m_blk) * BM;
+      const int64_t tile_col0 = static_cast<int64_t>(n_blk) * BN;
+      const int64_t cols_left = p.N - tile_col0;
+      const int n_sub = static_cast<int>(cols_left < BN ? (cols_left + 31) >> 5 : BN / 32);  // 32-column sub-chunks
+      int pos_j[8];
+      if (is_rope) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 cs = __ldg(tab + i);  // (cos0, sin0, cos1, sin1)
-              const float a0 = __uint_as_float(r[4 * i + 0]), b0 = __uint_as_float(r[4 * i + 1]);
-              const float a1 = __uint_as_float(r[4 * i + 2]), b1 = __uint_as_float(r[4 * i + 3]);
-              r[4 * i + 0] = __float_as_uint(a0 * cs.x - b0 * cs.y);
-              r[4 * i + 1] = __float_as_uint(b0 * cs.x + a0 * cs.y);
-              r[4 * i + 2] = __float_as_uint(a1 * cs.z - b1 * cs.w);
-              r[4 * i + 3] = __float_as_uint(b1 * cs.z + a1 * cs.w);
+        for (int j = 0; j < 8; ++j) pos_j[j] = static_cast<int>((row_base + lrow0 + 4 * j) % p.rope_T);
+      }
+      // coalesced fetch of sub-chunk `sc`'s global operand: dst[j] = piece `piece` of row lrow0 + 4j
+      auto fetch_aux = [&](float4(&dst)[8], int sc) {
+        const int64_t col0 = tile_col0 + sc * 32;
+        if (is_resid) {
+          const int64_t colp = col0 + piece * 4;
+          if (colp < p.N) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int64_t row = row_base + lrow0 + 4 * j;
+              if (row < p.M) dst[j] = __ldg(reinterpret_cast<const float4*>(p.R + row * p.ldc + colp));
             }
           }
-          __nv_bfloat16* cptr = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0;
+        } else if (is_rope && col0 < p.rope_cols) {
+          const int off = static_cast<int>(col0 % p.head_dim) + piece * 4;  // (cos,sin) pairs: 2 floats per 2 columns
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i * 8 < ncols) {
-              uint4 v;
-              v.x = pack_bf16x2(__uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1]));
-              v.y = pack_bf16x2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
-              v.z = pack_bf16x2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]));
-              v.w = pack_bf16x2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
-              *reinterpret_cast<uint4*>(cptr + i * 8) = v;
-            }
-          }
-        } else {
-          float* cptr = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
-          if (p.epilogue == PLM_EPI_RESID_F32) {
-            const float* rptr = p.R + row * p.ldc + col0;
+          for (int j = 0; j < 8; ++j)
+            dst[j] = __ldg(reinterpret_cast<const float4*>(p.rope + static_cast<int64_t>(pos_j[j]) * p.head_dim + off));
+        }
+      };
+      auto stage_aux = [&](uint8_t* buf, const float4(&src)[8]) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (i * 4 < ncols) {
-                const float4 rv = *reinterpret_cast<const float4*>(rptr + i * 4);
-                float4 v;
-                v.x = rv.x + __uint_as_float(r[4 * i + 0]);
-                v.y = rv.y + __uint_as_float(r[4 * i + 1]);
-                v.z = rv.z + __uint_as_float(r[4 * i + 2]);
-                v.w = rv.w + __uint_as_float(r[4 * i + 3]);
-                *reinterpret_cast<float4*>(cptr + i * 4) = v;
-              }
-            }
-          } else if (p.epilogue == PLM_EPI_ATOMIC_F32) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (i * 4 < ncols)
-                red_add_f32x4(cptr + i * 4, __uint_as_float(r[4 * i + 0]), __uint_as_float(r[4 * i + 1]),
-                              __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (i * 4 < ncols) {
-                float4 v;
-                v.x = __uint_as_float(r[4 * i + 0]);
-                v.y = __uint_as_float(r[4 * i + 1]);
-                v.z = __uint_as_float(r[4 * i + 2]);
-                v.w = __uint_as_float(r[4 * i + 3]);
-                *reinterpret_cast<float4*>(cptr + i * 4) = v;
-              }
-            }
-          }
+        for (int j = 0; j < 8; ++j) {
+          const int rr = lrow0 + 4 * j;
+          *reinterpret_cast<float4*>(buf + rr * 128 + ((piece ^ (rr & 7)) << 4)) = src[j];
+        }
+      };
+      if (is_resid) {  // pull this thread's residual row segment into L2 while the main loop still runs
+        const int64_t row = row_base + r_tile;
+        if (row < p.M) {
+          for (int sc = 0; sc < n_sub; ++sc)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R + row * p.ldc + tile_col0 + sc * 32));
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[a]);
+      float4 nxt[8];
+      fetch_aux(nxt, 0);
+      mbar_wait(&tfull[a], aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
+      const int r0 = static_cast<int>(row_base);
+      if (out_bf16) {
+        const int n_chunks = (n_sub + 1) >> 1;  // 64 bf16 columns per staging row
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+          uint8_t* buf = sEpi + (chunk_no & 1) * EPI_BUF_BYTES;
+          if (elected) bulk_wait_group_read<1>();  // the store that last read this staging tile has drained it
+          named_bar_sync(1, GEMM_EPI_WARPS * 32);
+          uint32_t o[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int sc = 2 * c + h;
+            if (sc < n_sub) {  // warp-uniform
+              const bool rope_on = is_rope && (tile_col0 + sc * 32 < p.rope_cols);
+              if (rope_on) {
+                stage_aux(buf, nxt);
+                __syncwarp();
+              }
+              if (sc + 1 < n_sub) fetch_aux(nxt, sc + 1);
+              uint32_t r[32];
+              tmem_ld32(t_row + sc * 32, r);
+              tmem_ld_wait();
+              if (rope_on) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float4 cs = *reinterpret_cast<const float4*>(buf + own_off + ((i ^ own_sw) << 4));
+                  const float a0 = __uint_as_float(r[4 * i + 0]), b0 = __uint_as_float(r[4 * i + 1]);
+                  const float a1 = __uint_as_float(r[4 * i + 2]), b1 = __uint_as_float(r[4 * i + 3]);
+                  r[4 * i + 0] = __float_as_uint(a0 * cs.x - b0 * cs.y);
+                  r[4 * i + 1] = __float_as_uint(b0 * cs.x + a0 * cs.y);
+                  r[4 * i + 2] = __float_as_uint(a1 * cs.z - b1 * cs.w);
+                  r[4 * i + 3] = __float_as_uint(b1 * cs.z + a1 * cs.w);
+                }
+                __syncwarp();  // every lane has read its (cos,sin) row before the tile is overwritten
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                o[16 * h + i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            }
+          }
+          if (c == n_chunks - 1) {  // last read of this accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(buf + own_off + ((i ^ own_sw) << 4)) =
+                make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          fence_proxy_async_smem();
+          named_bar_sync(1, GEMM_EPI_WARPS * 32);
+          if (elected && !(p.debug & 2)) {
+            tma_store_2d(&tmC, buf, static_cast<int>(tile_col0) + c * 64, r0);
+            bulk_commit_group();
+          }
+          ++chunk_no;
+        }
+      } else {
+#pragma unroll 1
+        for (int sc = 0; sc < n_sub; ++sc) {  // 32 fp32 columns per staging row
+          uint8_t* buf = sEpi + (chunk_no & 1) * EPI_BUF_BYTES;
+          if (elected) bulk_wait_group_read<1>();
+          named_bar_sync(1, GEMM_EPI_WARPS * 32);
+          if (is_resid) {
+            stage_aux(buf, nxt);
+            __syncwarp();
+          }
+          if (sc + 1 < n_sub) fetch_aux(nxt, sc + 1);
+          uint32_t r[32];
+          tmem_ld32(t_row + sc * 32, r);
+          tmem_ld_wait();
+          if (sc == n_sub - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4* slot = reinterpret_cast<float4*>(buf + own_off + ((i ^ own_sw) << 4));
+            float4 v;
+            v.x = __uint_as_float(r[4 * i + 0]);
+            v.y = __uint_as_float(r[4 * i + 1]);
+            v.z = __uint_as_float(r[4 * i + 2]);
+            v.w = __uint_as_float(r[4 * i + 3]);
+            if (is_resid) {  // the slot holds this row's residual piece; only this thread touches it from here on
+              const float4 x = *slot;
+              v.x += x.x;
+              v.y += x.y;
+              v.z += x.z;
+              v.w += x.w;
+            }
+            *slot = v;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, GEMM_EPI_WARPS * 32);
+          if (elected && !(p.debug & 2)) {
+            const int c0 = static_cast<int>(tile_col0) + sc * 32;
+            if (p.epilogue == PLM_EPI_ATOMIC_F32)
+              tma_reduce_add_2d(&tmC, buf, c0, r0);
+            else
+              tma_store_2d(&tmC, buf, c0, r0);
+            bulk_commit_group();
+          }
+          ++chunk_no;
+        }
+      }
     }
+    if (elected) bulk_wait_group<0>();  // every store has landed before the CTA may exit
   }
 
   tc_fence_before();
@@ -308,7 +405,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int BN, bool A_K, bool B_K, int CL>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                       cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -332,7 +430,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_K, B_K, CL>, tmA, tmB, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_K, B_K, CL>, tmA, tmB, tmC, p);
   if (e != cudaSuccess) return fail(PLM_ERR_CUDA, "gemm_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_kernel");
 }
@@ -379,6 +477,7 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   p.rope_cols = a->rope_cols;
   p.rope_T = a->rope_T;
   p.head_dim = a->head_dim;
+  p.debug = env_int("PLM_GEMM_DEBUG", 0);
   p.kblocks = static_cast<int>((a->K + BK - 1) / BK);
   p.num_m = static_cast<int>((a->M + BM - 1) / BM);
 
@@ -435,8 +534,13 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   }
   p.splits = splits;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   int rc;
+  if (a->epilogue == PLM_EPI_BF16 || a->epilogue == PLM_EPI_BF16_ROPE)
+    rc = make_tmap_bf16_2d(&tmC, a->C, a->M, a->N, a->ldc, BM, 64);
+  else
+    rc = make_tmap_f32_2d(&tmC, a->C, a->M, a->N, a->ldc, BM, 32);
+  if (rc != PLM_OK) return rc;
   if (a_k)
     rc = make_tmap_bf16_2d(&tmA, a->A, a->M, a->K, a->lda, BM, 64);
   else
@@ -449,10 +553,10 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   if (rc != PLM_OK) return rc;
 
 #define PLM_DISPATCH(BN_, CL_)                                                        \
-  if (a_k && b_k) return launch_gemm<BN_, true, true, CL_>(tmA, tmB, p, stream);      \
-  if (a_k && !b_k) return launch_gemm<BN_, true, false, CL_>(tmA, tmB, p, stream);    \
-  if (!a_k && b_k) return launch_gemm<BN_, false, true, CL_>(tmA, tmB, p, stream);    \
-  return launch_gemm<BN_, false, false, CL_>(tmA, tmB, p, stream);
+  if (a_k && b_k) return launch_gemm<BN_, true, true, CL_>(tmA, tmB, tmC, p, stream);      \
+  if (a_k && !b_k) return launch_gemm<BN_, true, false, CL_>(tmA, tmB, tmC, p, stream);    \
+  if (!a_k && b_k) return launch_gemm<BN_, false, true, CL_>(tmA, tmB, tmC, p, stream);    \
+  return launch_gemm<BN_, false, false, CL_>(tmA, tmB, tmC, p, stream);
   if (bn == 256 && cl == 2) {
     PLM_DISPATCH(256, 2)
   } else if (bn == 256) {

@@ -450,6 +450,39 @@ def case_gemm_sustained():
   return out
 
 
+def case_gemm_epi_perf():
+  """Forward GEMMs with their fused epilogues at the 420M shapes (RoPE on q|k; fp32 residual add)."""
+  import torch
+  from plainlm_b200 import ops, _lib
+
+  dev = 'cuda'
+  M, d, F, T = 16384, 1024, 2816, 2048
+  bf = torch.bfloat16
+  x = torch.randn(M, d, device=dev).to(bf)
+  g = torch.randn(M, F, device=dev).to(bf)
+  wqkv = torch.randn(3 * d, d, device=dev).to(bf)
+  wout = torch.randn(d, d, device=dev).to(bf)
+  w2 = torch.randn(d, F, device=dev).to(bf)
+  qkv = torch.empty(M, 3 * d, device=dev, dtype=bf)
+  res = torch.randn(M, d, device=dev)
+  out = torch.empty(M, d, device=dev)
+  tab = _rope_table(64, T).to(dev)
+  cases = [
+    ('qkv + rope', lambda: ops.gemm(x, wqkv, qkv, epilogue=_lib.EPI_BF16_ROPE, rope_table=tab, rope_cols=2 * d, rope_T=T, head_dim=64), 2.0 * M * 3 * d * d),
+    ('qkv plain', lambda: ops.gemm(x, wqkv, qkv), 2.0 * M * 3 * d * d),
+    ('out + resid', lambda: ops.gemm(x, wout, out, epilogue=_lib.EPI_RESID_F32, residual=res), 2.0 * M * d * d),
+    ('fc2 + resid', lambda: ops.gemm(g, w2, out, epilogue=_lib.EPI_RESID_F32, residual=res), 2.0 * M * d * F),
+  ]
+  results = []
+  for dbg in (0, 1, 2, 3):
+    os.environ['PLM_GEMM_DEBUG'] = str(dbg)
+    for n, fn, fl in cases:
+      ms = _time(fn, 10)
+      results.append({'case': f'{n} dbg{dbg}', 'ms': round(ms, 4), 'tflops': round(fl / ms / 1e9, 0)})
+  os.environ.pop('PLM_GEMM_DEBUG')
+  return results
+
+
 def case_bw_perf():
   """Achieved GB/s of the bandwidth kernels at the 420M shapes (algorithmic bytes / CUDA-event time)."""
   import torch
@@ -576,6 +609,7 @@ CASES['bandwidth'] = case_bandwidth
 CASES['gemm_perf'] = case_gemm_perf
 CASES['attn_perf'] = case_attn_perf
 CASES['bw_perf'] = case_bw_perf
+CASES['gemm_epi_perf'] = case_gemm_epi_perf
 CASES['gemm_sustained'] = case_gemm_sustained
 
 
