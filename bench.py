@@ -276,6 +276,16 @@ def run_ours(args):
   ftok = flops_per_token(c)
   peaks = load_peaks()
 
+  if rank == 0 and os.environ.get('PLM_BENCH_DETAIL'):  # per-(kernel, shape) table of the instrumented step
+    rows = []
+    for (name, tag), (cnt, ms) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
+      kind, work = op_work(name, tag, c)
+      rate = work * cnt / (ms / 1e3) / (1e12 if kind == 'tensor' else 1e9)
+      rows.append(f'{name:22s} {str(tag):44s} calls {cnt:4d}  total {ms:8.3f} ms  avg {ms / cnt * 1e3:8.1f} us  '
+                  f'{rate:8.1f} {"TF/s" if kind == "tensor" else "GB/s"}')
+    with open(os.environ['PLM_BENCH_DETAIL'], 'w') as f:
+      f.write('\n'.join(rows) + '\n')
+
   if rank == 0:
     total_ms = sum(v[1] for v in summ.values())
     by_kernel = {}

@@ -28,7 +28,7 @@ extern "C" {
 #define PLM_ERR_CUDA (-2)        /* CUDA runtime / driver error while encoding a descriptor or launching */
 #define PLM_ERR_UNSUPPORTED (-3) /* shape outside what the sm_100a kernels implement                     */
 
-#define PLM_ABI_VERSION 1
+#define PLM_ABI_VERSION 2
 
 typedef void* plm_stream_t;
 
@@ -56,6 +56,10 @@ int plm_device_check(void);
  *   PLM_EPI_F32         C (fp32)  = acc
  *   PLM_EPI_RESID_F32   C (fp32)  = R (fp32, same ld as C) + acc         (models/transformer.py:81-82 residual add)
  *   PLM_EPI_ATOMIC_F32  C (fp32) += acc with red.global.add (split-K capable; fp32 .grad accumulation)
+ *   PLM_EPI_BF16_SWIGLU C (bf16)  = acc  AND  C2 (bf16 [M, N/2], ld = ldc2) = silu(C[:, :N/2]) * C[:, N/2:]
+ *                       (models/components.py:55-56: the GLU gate applied to fc1's output u = [a | z] while the tile is
+ *                       still on chip; silu is evaluated on the bf16-rounded a, z exactly like plm_swiglu_fwd).
+ *                       Needs b_kmajor = 1 and (N/2) % 128 == 0.
  * splits > 1 partitions K and is only legal with PLM_EPI_ATOMIC_F32.  splits <= 0 lets the library choose.
  */
 #define PLM_EPI_BF16 0
@@ -63,6 +67,7 @@ int plm_device_check(void);
 #define PLM_EPI_F32 2
 #define PLM_EPI_RESID_F32 3
 #define PLM_EPI_ATOMIC_F32 4
+#define PLM_EPI_BF16_SWIGLU 5
 
 typedef struct plm_gemm_args {
   const void* A; /* bf16 */
@@ -76,6 +81,8 @@ typedef struct plm_gemm_args {
   int32_t epilogue;
   int32_t splits;
   int32_t rope_cols, rope_T, head_dim;
+  void* C2;     /* bf16 [M, N/2], PLM_EPI_BF16_SWIGLU only */
+  int64_t ldc2; /* leading dimension of C2 (elements) */
 } plm_gemm_args;
 
 int plm_gemm_bf16(const plm_gemm_args* args, plm_stream_t stream);

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libplainlm_b200.so')
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 
 PLM_OK = 0
-EPI_BF16, EPI_BF16_ROPE, EPI_F32, EPI_RESID_F32, EPI_ATOMIC_F32 = range(5)
+EPI_BF16, EPI_BF16_ROPE, EPI_F32, EPI_RESID_F32, EPI_ATOMIC_F32, EPI_BF16_SWIGLU = range(6)
 SUMSQ_WORKSPACE = 1024
 
 c_void_p, c_int32, c_int64, c_float = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
@@ -25,6 +25,7 @@ class GemmArgs(ctypes.Structure):
     ('lda', c_int64), ('ldb', c_int64), ('ldc', c_int64),
     ('a_kmajor', c_int32), ('b_kmajor', c_int32), ('epilogue', c_int32), ('splits', c_int32),
     ('rope_cols', c_int32), ('rope_T', c_int32), ('head_dim', c_int32),
+    ('C2', c_void_p), ('ldc2', c_int64),
   ]  # fmt: skip
 
 
@@ -87,7 +88,7 @@ def load():
     fn = getattr(lib, name)  # AttributeError if the symbol is missing
     fn.restype = restype
     fn.argtypes = argtypes
-  if lib.plm_abi_version() != 1:
+  if lib.plm_abi_version() != 2:
     raise RuntimeError('libplainlm_b200.so ABI version mismatch')
   _lib = lib
   return lib

@@ -8,8 +8,6 @@
 
 namespace plm {
 
-__device__ __forceinline__ float sigmoidf_fast(float a) { return 1.0f / (1.0f + __expf(-a)); }
-
 // ------------------------------------------------------------------------------------------- SwiGLU
 // u = [a | z] per row (2F columns); h = silu(a) * z.  One thread per 8 hidden elements.
 __global__ void __launch_bounds__(256)

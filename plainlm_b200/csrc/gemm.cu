@@ -36,8 +36,10 @@ struct GemmParams {
   int epilogue;
   int splits;
   int rope_cols, rope_T, head_dim;
+  int glu_F;  // PLM_EPI_BF16_SWIGLU: F = N/2; tile n covers gate columns [128n, 128n+128) and up columns F + the same
   int num_m, num_n, kblocks;
-  int debug;      // diagnostics only (PLM_GEMM_DEBUG): 1 = skip epilogue operand loads, 2 = skip stores
+  int debug;      // diagnostics only (PLM_GEMM_DEBUG): 1 = skip epilogue operand loads, 2 = skip stores,
+                  // 4 = skip B tile loads, 8 = skip A tile loads (results are then garbage; timing experiments only)
   int n_fastest;  // tile rasterisation: 0 = consecutive tiles walk M (B tile reused), 1 = walk N (A tile reused)
 };
 
@@ -78,7 +80,7 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int rank
 template <int BN, bool A_K, bool B_K, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   static_assert(CL == 1 || CL == 2, "cluster of 1 or 2 CTAs");
@@ -105,6 +107,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
+    tma_prefetch_desc(&tmC2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], CL);  // CL = 2: the stage is overwritten in BOTH CTAs, so both must have consumed it
@@ -135,18 +138,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         decode_work<CL>(p, w, rank, m_blk, n_blk, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          mbar_arrive_expect_tx(&full[s], ((p.debug & 8) ? 0 : Cfg::A_BYTES) + ((p.debug & 4) ? 0 : Cfg::B_BYTES));
           uint8_t* a_dst = sA + s * Cfg::A_BYTES;
           uint8_t* b_dst = sB + s * Cfg::B_BYTES;
-          if (A_K) {
+          if (p.debug & 8) {
+          } else if (A_K) {
             tma_load_2d(a_dst, &tmA, &full[s], kb * BK, m_blk * BM);
           } else {
 #pragma unroll
             for (int g = 0; g < BM / 64; ++g)
               tma_load_2d(a_dst + g * (BK * 128), &tmA, &full[s], m_blk * BM + g * 64, kb * BK);
           }
-          if (CL == 1) {
-            if (B_K) {
+          if (p.debug & 4) {
+          } else if (CL == 1) {
+            if (B_K && p.glu_F) {  // gate rows then up rows (the tensor map's box is BN/2 rows here)
+              tma_load_2d(b_dst, &tmB, &full[s], kb * BK, n_blk * (BN / 2));
+              tma_load_2d(b_dst + (BN / 2) * 128, &tmB, &full[s], kb * BK, p.glu_F + n_blk * (BN / 2));
+            } else if (B_K) {
               tma_load_2d(b_dst, &tmB, &full[s], kb * BK, n_blk * BN);
             } else {
 #pragma unroll
@@ -157,7 +165,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // each CTA fetches HALF of the shared B tile and multicasts it into both CTAs' stage buffers:
             // L2 -> SM traffic per CTA drops from A + B to A + B/2
             if (B_K) {
-              tma_load_2d_mc(b_dst + rank * (BN / 2) * 128, &tmB, &full[s], kb * BK, n_blk * BN + rank * (BN / 2), 0x3);
+              const int b_row = p.glu_F ? (rank ? p.glu_F : 0) + n_blk * (BN / 2) : n_blk * BN + rank * (BN / 2);
+              tma_load_2d_mc(b_dst + rank * (BN / 2) * 128, &tmB, &full[s], kb * BK, b_row, 0x3);
             } else {
 #pragma unroll
               for (int g = 0; g < BN / 128; ++g) {
@@ -273,11 +282,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           *reinterpret_cast<float4*>(buf + rr * 128 + ((piece ^ (rr & 7)) << 4)) = src[j];
         }
       };
-      if (is_resid) {  // pull this thread's residual row segment into L2 while the main loop still runs
-        const int64_t row = row_base + r_tile;
-        if (row < p.M) {
-          for (int sc = 0; sc < n_sub; ++sc)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R + row * p.ldc + tile_col0 + sc * 32));
+      if (is_resid) {  // pull residual row segments into L2 well ahead of their use: this tile's on the first
+                       // iteration, and always the NEXT tile's (its main loop has not even finished yet)
+        auto l2_prefetch_rows = [&](int mb, int nb) {
+          const int64_t row = static_cast<int64_t>(mb) * BM + r_tile;
+          const int64_t c0 = static_cast<int64_t>(nb) * BN;
+          if (row < p.M) {
+            for (int sc = 0; sc < BN / 32 && c0 + sc * 32 < p.N; ++sc)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.R + row * p.ldc + c0 + sc * 32));
+          }
+        };
+        if (it == 0) l2_prefetch_rows(m_blk, n_blk);
+        if (w + num_clusters < total) {
+          int m2, n2, k0, k1;
+          decode_work<CL>(p, w + num_clusters, rank, m2, n2, k0, k1);
+          l2_prefetch_rows(m2, n2);
         }
       }
       float4 nxt[8];
@@ -286,7 +305,59 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN;
       const int r0 = static_cast<int>(row_base);
-      if (out_bf16) {
+      if (p.epilogue == PLM_EPI_BF16_SWIGLU) {
+        // accumulator columns [0,128) = gate a, [128,256) = up z.  Per 64-column group: write a and z to their places in
+        // u, then h = silu(a) * z (from the bf16-rounded values, as the stand-alone kernel computes it) to C2.
+        auto emit = [&](const uint32_t(&o)[32], const CUtensorMap* map, int c0) {
+          uint8_t* buf = sEpi + (chunk_no & 1) * EPI_BUF_BYTES;
+          if (elected) bulk_wait_group_read<1>();
+          named_bar_sync(1, GEMM_EPI_WARPS * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(buf + own_off + ((i ^ own_sw) << 4)) =
+                make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          fence_proxy_async_smem();
+          named_bar_sync(1, GEMM_EPI_WARPS * 32);
+          if (elected && !(p.debug & 2)) {
+            tma_store_2d(map, buf, c0, r0);
+            bulk_commit_group();
+          }
+          ++chunk_no;
+        };
+        const int gate_col0 = n_blk * (BN / 2);
+#pragma unroll 1
+        for (int j = 0; j < BN / 128; ++j) {
+          uint32_t oa[32], oz[32];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[32];
+            tmem_ld32(t_row + j * 64 + h * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              oa[16 * h + i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            tmem_ld32(t_row + BN / 2 + j * 64 + h * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              oz[16 * h + i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+          }
+          if (j == BN / 128 - 1) {  // last read of this accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[a]);
+          }
+          emit(oa, &tmC, gate_col0 + j * 64);
+          emit(oz, &tmC, p.glu_F + gate_col0 + j * 64);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float a0 = bf16_lo(oa[i]), a1 = bf16_hi(oa[i]);
+            const float z0 = bf16_lo(oz[i]), z1 = bf16_hi(oz[i]);
+            oa[i] = pack_bf16x2(a0 * sigmoidf_fast(a0) * z0, a1 * sigmoidf_fast(a1) * z1);
+          }
+          emit(oa, &tmC2, gate_col0 + j * 64);
+        }
+      } else if (out_bf16) {
         const int n_chunks = (n_sub + 1) >> 1;  // 64 bf16 columns per staging row
 #pragma unroll 1
         for (int c = 0; c < n_chunks; ++c) {
@@ -405,8 +476,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int BN, bool A_K, bool B_K, int CL>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
+                       const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -430,7 +501,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_K, B_K, CL>, tmA, tmB, tmC, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_K, B_K, CL>, tmA, tmB, tmC, tmC2, p);
   if (e != cudaSuccess) return fail(PLM_ERR_CUDA, "gemm_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_kernel");
 }
@@ -454,7 +525,13 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   PLM_REQUIRE(aligned16(a->A) && aligned16(a->B) && aligned16(a->C), "gemm: operands must be 16-byte aligned");
   PLM_REQUIRE(a->N % 8 == 0 && a->lda % 8 == 0 && a->ldb % 8 == 0 && a->ldc % 8 == 0,
               "gemm: N and leading dimensions must be multiples of 8");
-  PLM_REQUIRE(a->epilogue >= PLM_EPI_BF16 && a->epilogue <= PLM_EPI_ATOMIC_F32, "gemm: bad epilogue %d", a->epilogue);
+  PLM_REQUIRE(a->epilogue >= PLM_EPI_BF16 && a->epilogue <= PLM_EPI_BF16_SWIGLU, "gemm: bad epilogue %d", a->epilogue);
+  const bool glu = a->epilogue == PLM_EPI_BF16_SWIGLU;
+  if (glu) {
+    PLM_REQUIRE(a->b_kmajor != 0 && a->N % 256 == 0, "gemm: the SwiGLU epilogue needs a K-major B and N/2 %% 128 == 0");
+    PLM_REQUIRE(a->C2 && aligned16(a->C2) && a->ldc2 % 8 == 0 && a->ldc2 >= a->N / 2,
+                "gemm: SwiGLU output C2 missing/misaligned");
+  }
   if (a->epilogue == PLM_EPI_RESID_F32) PLM_REQUIRE(a->R && aligned16(a->R), "gemm: residual pointer missing/misaligned");
   if (a->epilogue == PLM_EPI_BF16_ROPE) {
     PLM_REQUIRE(a->rope_table && aligned16(a->rope_table), "gemm: rope table missing/misaligned");
@@ -477,6 +554,7 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   p.rope_cols = a->rope_cols;
   p.rope_T = a->rope_T;
   p.head_dim = a->head_dim;
+  p.glu_F = glu ? static_cast<int>(a->N / 2) : 0;
   p.debug = env_int("PLM_GEMM_DEBUG", 0);
   p.kblocks = static_cast<int>((a->K + BK - 1) / BK);
   p.num_m = static_cast<int>((a->M + BM - 1) / BM);
@@ -489,6 +567,7 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
     const int forced = env_int("PLM_GEMM_BN", 0);
     if (forced == 128 || forced == 256) bn = forced;
   }
+  if (glu) bn = 256;  // 128 gate + 128 up columns per tile
   // Rasterisation: the ~148 tiles in flight should share the operand that does NOT fit in L2.  Walking M keeps one
   // B tile hot and streams A once per N-block (fine when A fits in L2); walking N reads each A row-block once.
   {
@@ -534,29 +613,34 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   }
   p.splits = splits;
 
-  CUtensorMap tmA, tmB, tmC;
+  CUtensorMap tmA, tmB, tmC, tmC2;
   int rc;
-  if (a->epilogue == PLM_EPI_BF16 || a->epilogue == PLM_EPI_BF16_ROPE)
+  if (a->epilogue == PLM_EPI_BF16 || a->epilogue == PLM_EPI_BF16_ROPE || glu)
     rc = make_tmap_bf16_2d(&tmC, a->C, a->M, a->N, a->ldc, BM, 64);
   else
     rc = make_tmap_f32_2d(&tmC, a->C, a->M, a->N, a->ldc, BM, 32);
   if (rc != PLM_OK) return rc;
+  tmC2 = tmC;
+  if (glu) {
+    rc = make_tmap_bf16_2d(&tmC2, a->C2, a->M, a->N / 2, a->ldc2, BM, 64);
+    if (rc != PLM_OK) return rc;
+  }
   if (a_k)
     rc = make_tmap_bf16_2d(&tmA, a->A, a->M, a->K, a->lda, BM, 64);
   else
     rc = make_tmap_bf16_2d(&tmA, a->A, a->K, a->M, a->lda, BK, 64);
   if (rc != PLM_OK) return rc;
   if (b_k)
-    rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, bn / cl, 64);  // cluster: each CTA fetches half the rows
+    rc = make_tmap_bf16_2d(&tmB, a->B, a->N, a->K, a->ldb, glu ? bn / 2 : bn / cl, 64);  // cluster: each CTA fetches half the rows
   else
     rc = make_tmap_bf16_2d(&tmB, a->B, a->K, a->N, a->ldb, BK, 64);
   if (rc != PLM_OK) return rc;
 
 #define PLM_DISPATCH(BN_, CL_)                                                        \
-  if (a_k && b_k) return launch_gemm<BN_, true, true, CL_>(tmA, tmB, tmC, p, stream);      \
-  if (a_k && !b_k) return launch_gemm<BN_, true, false, CL_>(tmA, tmB, tmC, p, stream);    \
-  if (!a_k && b_k) return launch_gemm<BN_, false, true, CL_>(tmA, tmB, tmC, p, stream);    \
-  return launch_gemm<BN_, false, false, CL_>(tmA, tmB, tmC, p, stream);
+  if (a_k && b_k) return launch_gemm<BN_, true, true, CL_>(tmA, tmB, tmC, tmC2, p, stream);      \
+  if (a_k && !b_k) return launch_gemm<BN_, true, false, CL_>(tmA, tmB, tmC, tmC2, p, stream);    \
+  if (!a_k && b_k) return launch_gemm<BN_, false, true, CL_>(tmA, tmB, tmC, tmC2, p, stream);    \
+  return launch_gemm<BN_, false, false, CL_>(tmA, tmB, tmC, tmC2, p, stream);
   if (bn == 256 && cl == 2) {
     PLM_DISPATCH(256, 2)
   } else if (bn == 256) {

@@ -248,6 +248,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// MUFU.EX2 + MUFU.RCP (2 ulp; the result is rounded to bf16 by every caller)
+__device__ __forceinline__ float sigmoidf_fast(float a) { return __fdividef(1.0f, 1.0f + __expf(-a)); }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 

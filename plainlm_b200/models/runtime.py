@@ -14,8 +14,9 @@ Layout in HBM (M = B*T tokens, d model dim, F GLU hidden, V vocab):
                   x_mid fp32[M,d], h2 bf16[M,d], rstd2[M], u bf16[M,2F], g bf16[M,F]
 """
 
-import torch
+import os
 
+import torch
 from .. import _lib, ops
 
 bf16, f32 = torch.bfloat16, torch.float32
@@ -193,8 +194,8 @@ class TrainRuntime:
       ops.attn_fwd(ws.qkv[l], ws.attn[l], ws.lse[l], B, T, H, hd, seg_start=seg_start)
       ops.gemm(ws.attn[l], W[pre + 'attn.w_out.weight'], ws.x_mid[l], epilogue=_lib.EPI_RESID_F32, residual=ws.x[l])
       ops.rmsnorm_fwd(ws.x_mid[l], P[pre + 'mlp_norm.weight'], ws.h2[l], ws.rstd2[l], m.eps)
-      ops.gemm(ws.h2[l], W[pre + 'mlp.fc1.weight'], ws.u[l])
-      ops.swiglu_fwd(ws.u[l], ws.g[l])
+      # fc1 with the GLU gate applied while the tile is on chip: writes u = [a | z] (saved for backward) and g = silu(a) z
+      ops.gemm(ws.h2[l], W[pre + 'mlp.fc1.weight'], ws.u[l], epilogue=_lib.EPI_BF16_SWIGLU, out2=ws.g[l])
       ops.gemm(ws.g[l], W[pre + 'mlp.fc2.weight'], ws.x[l + 1], epilogue=_lib.EPI_RESID_F32, residual=ws.x_mid[l])
     ops.rmsnorm_fwd(ws.x[L], P['out_norm.weight'], ws.hf, ws.rstd_f, m.eps)
     return ws.hf
@@ -269,6 +270,9 @@ class TrainRuntime:
     """grad[name] += dy^T x  (contraction over tokens, both operands read in place as MN-major), on the side stream:
     nothing downstream in backward needs it, so it overlaps the main stream and fills the idle SMs of its kernel tails.
     `guard` names the dy buffer: whoever overwrites it later first waits for this GEMM (_release)."""
+    if os.environ.get('PLM_NO_SIDE_STREAM'):  # profiling aid: serialise so per-kernel events are not overlapped
+      ops.gemm(dy, x, self.G[name], a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ATOMIC_F32, splits=0)
+      return
     main = torch.cuda.current_stream()
     ready = torch.cuda.Event()
     ready.record(main)

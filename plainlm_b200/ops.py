@@ -37,7 +37,7 @@ bf16, f32 = torch.bfloat16, torch.float32
 
 # ---------------------------------------------------------------------------------------------- GEMM
 def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_BF16, residual=None, rope_table=None,
-         rope_cols=0, rope_T=0, head_dim=0, splits=1):
+         rope_cols=0, rope_T=0, head_dim=0, splits=1, out2=None):
   """out[M,N] = contraction of a and b (see include/plainlm_b200.h, plm_gemm_bf16).
 
   a: [M,K] if a_kmajor else [K,M];  b: [N,K] if b_kmajor else [K,N];  bf16, unit inner stride.
@@ -48,7 +48,7 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_BF16, res
   N, Kb = (b.shape[0], b.shape[1]) if b_kmajor else (b.shape[1], b.shape[0])
   if K != Kb or out.shape[0] != M or out.shape[1] != N:
     raise ValueError(f'plainlm_b200.gemm: shape mismatch a={tuple(a.shape)} b={tuple(b.shape)} out={tuple(out.shape)}')
-  out_dtype = bf16 if epilogue in (_lib.EPI_BF16, _lib.EPI_BF16_ROPE) else f32
+  out_dtype = bf16 if epilogue in (_lib.EPI_BF16, _lib.EPI_BF16_ROPE, _lib.EPI_BF16_SWIGLU) else f32
   args = GemmArgs()
   args.A, args.B, args.C = _ptr(a, bf16, 'a'), _ptr(b, bf16, 'b'), _ptr(out, out_dtype, 'out')
   if residual is not None:
@@ -61,6 +61,10 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_BF16, res
   args.a_kmajor, args.b_kmajor = int(a_kmajor), int(b_kmajor)
   args.epilogue, args.splits = epilogue, splits
   args.rope_cols, args.rope_T, args.head_dim = rope_cols, rope_T, head_dim
+  if epilogue == _lib.EPI_BF16_SWIGLU:
+    if out2 is None or out2.shape[0] != M or out2.shape[1] * 2 != N:
+      raise ValueError('plainlm_b200.gemm: the SwiGLU epilogue needs out2 of shape [M, N/2]')
+    args.C2, args.ldc2 = _ptr(out2, bf16, 'out2'), _rowmajor_ld(out2, 'out2')
   check(lib.plm_gemm_bf16(ctypes.byref(args), _stream()), 'plm_gemm_bf16')
   return out
 

@@ -75,6 +75,30 @@ def test_gemm_epilogues(bn, monkeypatch):
   assert_close(outb[:, 512:], ref[:, 512:], BF16_RTOL, what='rope epilogue v untouched')
 
 
+@pytest.mark.parametrize('M,F,K', [(128, 128, 64), (256, 256, 128), (328, 384, 200), (2048, 2816, 1024)])
+def test_gemm_swiglu_epilogue(M, F, K):
+  """fc1 with the GLU gate applied in the epilogue (models/components.py:55-56): u must equal the plain GEMM bit for
+  bit, h must equal the stand-alone SwiGLU kernel on that u bit for bit, and both must match the oracle."""
+  ops, _lib = _ops()
+  g = torch.Generator().manual_seed(M + F)
+  A = (torch.randn(M, K, generator=g) * 0.5).to(bf16)
+  B = (torch.randn(2 * F, K, generator=g) * 0.5).to(bf16)
+  a, b = A.to(DEV), B.to(DEV)
+  u_plain = torch.empty(M, 2 * F, device=DEV, dtype=bf16)
+  ops.gemm(a, b, u_plain)
+  h_plain = torch.empty(M, F, device=DEV, dtype=bf16)
+  ops.swiglu_fwd(u_plain, h_plain)
+  u = torch.full((M, 2 * F), float('nan'), device=DEV, dtype=bf16)
+  h = torch.full((M, F), float('nan'), device=DEV, dtype=bf16)
+  ops.gemm(a, b, u, epilogue=_lib.EPI_BF16_SWIGLU, out2=h)
+  assert torch.equal(u, u_plain)
+  assert torch.equal(h, h_plain)
+  ref_u = A.float() @ B.float().t()
+  assert_close(u, ref_u, BF16_RTOL, what='u')
+  ub = u.float().cpu()
+  assert_close(h, torch.nn.functional.silu(ub[:, :F]) * ub[:, F:], BF16_RTOL, what='h')
+
+
 def test_gemm_lm_head_shape_sampled():
   """Full LM-head shape of the 420M config (16384 x 50280 x 1024): spot-check entries against fp64 dot products and
   the ragged vocabulary tail (50280 = 196*256 + 104)."""
@@ -102,6 +126,9 @@ def test_gemm_rejects_bad_arguments():
     ops.gemm(a, b, torch.zeros(128, 100, device=DEV, dtype=bf16))
   with pytest.raises(PlmError, match='split-K'):
     ops.gemm(a, a, torch.zeros(128, 128, device=DEV, dtype=bf16), splits=2)
+  with pytest.raises(PlmError, match='SwiGLU'):  # N/2 = 64 is not a multiple of 128
+    ops.gemm(a, a, torch.zeros(128, 128, device=DEV, dtype=bf16), epilogue=_lib.EPI_BF16_SWIGLU,
+             out2=torch.zeros(128, 64, device=DEV, dtype=bf16))
 
 
 # ------------------------------------------------------------------------------------------- reference modules

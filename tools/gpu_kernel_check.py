@@ -463,6 +463,8 @@ def case_gemm_epi_perf():
   wqkv = torch.randn(3 * d, d, device=dev).to(bf)
   wout = torch.randn(d, d, device=dev).to(bf)
   w2 = torch.randn(d, F, device=dev).to(bf)
+  w1 = torch.randn(2 * F, d, device=dev).to(bf)
+  u = torch.empty(M, 2 * F, device=dev, dtype=bf)
   qkv = torch.empty(M, 3 * d, device=dev, dtype=bf)
   res = torch.randn(M, d, device=dev)
   out = torch.empty(M, d, device=dev)
@@ -472,6 +474,9 @@ def case_gemm_epi_perf():
     ('qkv plain', lambda: ops.gemm(x, wqkv, qkv), 2.0 * M * 3 * d * d),
     ('out + resid', lambda: ops.gemm(x, wout, out, epilogue=_lib.EPI_RESID_F32, residual=res), 2.0 * M * d * d),
     ('fc2 + resid', lambda: ops.gemm(g, w2, out, epilogue=_lib.EPI_RESID_F32, residual=res), 2.0 * M * d * F),
+    ('fc1 + swiglu', lambda: ops.gemm(x, w1, u, epilogue=_lib.EPI_BF16_SWIGLU, out2=g), 2.0 * M * d * 2 * F),
+    ('fc1 plain', lambda: ops.gemm(x, w1, u), 2.0 * M * d * 2 * F),
+    ('swiglu alone', lambda: ops.swiglu_fwd(u, g), 2.0 * M * d * 2 * F),
   ]
   results = []
   for dbg in (0, 1, 2, 3):
@@ -480,6 +485,36 @@ def case_gemm_epi_perf():
       ms = _time(fn, 10)
       results.append({'case': f'{n} dbg{dbg}', 'ms': round(ms, 4), 'tflops': round(fl / ms / 1e9, 0)})
   os.environ.pop('PLM_GEMM_DEBUG')
+  return results
+
+
+def case_gemm_feed_probe():
+  """Is the main loop bound by operand delivery?  Store-less runs with the A and/or B tile loads removed."""
+  import torch
+  from plainlm_b200 import ops
+
+  dev = 'cuda'
+  M, d, F = 16384, 1024, 2816
+  bf = torch.bfloat16
+  x = torch.randn(M, d, device=dev).to(bf)
+  w1 = torch.randn(2 * F, d, device=dev).to(bf)
+  u = torch.empty(M, 2 * F, device=dev, dtype=bf)
+  du = torch.randn(M, 2 * F, device=dev).to(bf)
+  dx = torch.empty(M, d, device=dev, dtype=bf)
+  cases = [
+    ('fc1 fwd', lambda: ops.gemm(x, w1, u), 2.0 * M * 2 * F * d),
+    ('fc1 dgrad', lambda: ops.gemm(du, w1, dx, a_kmajor=True, b_kmajor=False), 2.0 * M * 2 * F * d),
+  ]
+  results = []
+  for cl in ('2', '1'):
+    os.environ['PLM_GEMM_CLUSTER'] = cl
+    for dbg in (0, 2, 6, 10, 14):
+      os.environ['PLM_GEMM_DEBUG'] = str(dbg)
+      for n, fn, fl in cases:
+        ms = _time(fn, 10)
+        results.append({'case': f'{n} cl{cl} dbg{dbg}', 'ms': round(ms, 4), 'tflops': round(fl / ms / 1e9, 0)})
+  os.environ.pop('PLM_GEMM_DEBUG')
+  os.environ.pop('PLM_GEMM_CLUSTER')
   return results
 
 
@@ -610,6 +645,7 @@ CASES['gemm_perf'] = case_gemm_perf
 CASES['attn_perf'] = case_attn_perf
 CASES['bw_perf'] = case_bw_perf
 CASES['gemm_epi_perf'] = case_gemm_epi_perf
+CASES['gemm_feed_probe'] = case_gemm_feed_probe
 CASES['gemm_sustained'] = case_gemm_sustained
 
 
