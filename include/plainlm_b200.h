@@ -187,8 +187,8 @@ int plm_cast_bf16_f32(const void* src, float* dst, int64_t n, float scale, plm_s
 int plm_seg_start_from_lengths(const int32_t* lengths, const int32_t* offsets, int32_t* seg_start, int32_t B,
                                int32_t T, plm_stream_t stream);
 
-/* Diagnostics: per-phase cycle counters of the attention-backward kernel (HOST pointer, n <= 32).  All zeros unless the
- * library was built with -DPLM_ATTN_TIMING; synchronises the device. */
+/* Diagnostics: clock64() stamps of the attention-backward kernel's phase boundaries (HOST pointer, n <= 256), written
+ * by one CTA when the environment variable PLM_ATTN_TRACE is set; all zeros otherwise.  Synchronises the device. */
 int plm_debug_counters(unsigned long long* out, int32_t n, int32_t reset);
 
 #ifdef __cplusplus

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace plm {
@@ -23,16 +24,17 @@ namespace plm {
 constexpr int AB_T = 128;   // tile edge (keys per CTA, queries per step)
 constexpr int AB_HD = 64;
 constexpr int AB_CWARPS = 16;    // compute warps: (TMEM lane quarter) x (column quarter)
-constexpr int AB_W_MMA_S = AB_CWARPS;       // issues S^T and dP^T
+constexpr int AB_W_MMA_S = AB_CWARPS;       // issues S^T, dP^T (early in a step) and dQ (late in the step)
 constexpr int AB_W_MMA_DV = AB_CWARPS + 1;  // issues dV
-constexpr int AB_W_MMA_DKQ = AB_CWARPS + 2; // issues dK and dQ
+constexpr int AB_W_MMA_DK = AB_CWARPS + 2;  // issues dK
 constexpr int AB_W_TMA = AB_CWARPS + 3;     // TMA producer
 constexpr int AB_THREADS = (AB_CWARPS + 4) * 32;
 constexpr int AB_STAGES = 3;       // Q_i / dO_i ring
 constexpr int AB_TILE = AB_T * AB_HD * 2;  // 16 KB
-// K, V, (Q,dO) x AB_STAGES, dS^T (2 blocks), vectors (lse2, delta, seg) x2 stages, barriers
+// K, V, (Q,dO) x AB_STAGES, dS^T (2 blocks), dQ staging (fp32 128 x 64), vectors (lse2, delta, seg) x stages, barriers
 constexpr int AB_VEC_BYTES = AB_STAGES * 3 * AB_T * 4;
-constexpr int AB_SMEM = AB_TILE * (2 + 2 * AB_STAGES + 2) + AB_VEC_BYTES + 256;
+constexpr int AB_DQ_STAGE = AB_T * AB_HD * 4;  // 32 KB: per lane quarter 2 column halves of [32 rows x 128 B], swizzled
+constexpr int AB_SMEM = AB_TILE * (2 + 2 * AB_STAGES + 2) + AB_DQ_STAGE + AB_VEC_BYTES + 256;
 
 __device__ __forceinline__ float ex2b(float x) {
   float y;
@@ -41,7 +43,13 @@ __device__ __forceinline__ float ex2b(float x) {
 }
 
 // Diagnostic counters exported through plm_debug_counters (unused in release builds: always zero).
-__device__ unsigned long long g_dbg_counters[32];
+__device__ unsigned long long g_dbg_counters[256];
+
+// PLM_ATTN_TRACE=1: one CTA stamps clock64() at its phase boundaries for four steady-state steps.
+#define AB_TR(slot_)                                                                 \
+  do {                                                                               \
+    if (tr_on && it >= 6 && it < 10 && lane == 0) g_dbg_counters[(slot_)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -150,29 +158,33 @@ __device__ __forceinline__ void store_bf16_row32(uint8_t* row_base, int r, int c
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const __grid_constant__ CUtensorMap tmDQ,
                 const float* __restrict__ lse, const float* __restrict__ delta, const int32_t* __restrict__ seg_start,
                 const float* __restrict__ rope, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_acc, int T,
-                int H, float scale, float scale_log2) {
+                int H, float scale, float scale_log2, int trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  const bool tr_on = trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == gridDim.z / 2;
   uint8_t* sK = smem;
   uint8_t* sV = smem + AB_TILE;
   uint8_t* sQ = smem + 2 * AB_TILE;                    // [AB_STAGES]
   uint8_t* sDO = smem + (2 + AB_STAGES) * AB_TILE;     // [AB_STAGES]
   uint8_t* sDS = smem + (2 + 2 * AB_STAGES) * AB_TILE; // dS^T: 2 blocks (q 0..63 | 64..127), each [128 kv rows x 128 B]
-  float* sLse = reinterpret_cast<float*>(smem + (4 + 2 * AB_STAGES) * AB_TILE);  // [AB_STAGES][128]  lse * log2(e)
+  uint8_t* sDQ = smem + (4 + 2 * AB_STAGES) * AB_TILE;  // dQ_i staging for the TMA reduce-add
+  float* sLse = reinterpret_cast<float*>(sDQ + AB_DQ_STAGE);  // [AB_STAGES][128]  lse * log2(e)
   float* sDelta = sLse + AB_STAGES * AB_T;                                         // [AB_STAGES][128]
   int32_t* sSeg = reinterpret_cast<int32_t*>(sDelta + AB_STAGES * AB_T);           // [AB_STAGES][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (4 + 2 * AB_STAGES) * AB_TILE + AB_VEC_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDQ + AB_DQ_STAGE + AB_VEC_BYTES);
   uint64_t* kv_full = bars + 0;
   uint64_t* qdo_full = bars + 1;                // [AB_STAGES]  TMA bytes of Q_i, dO_i + the 32 staging lanes
   uint64_t* qdo_empty = bars + 1 + AB_STAGES;   // [AB_STAGES]
   uint64_t* s_full = bars + 1 + 2 * AB_STAGES;  // S^T and dP^T of a step are in tensor memory
   uint64_t* pds_ready = s_full + 1;             // P^T (tensor memory) and dS^T (smem) of a step are written
-  uint64_t* dq_full = s_full + 2;               // dK/dQ MMAs of a step complete
+  uint64_t* dq_full = s_full + 2;               // dQ MMAs of a step complete
   uint64_t* dq_empty = s_full + 3;              // dQ of a step has been read out of tensor memory
   uint64_t* sdp_free = s_full + 4;              // compute warps have read S^T and dP^T out of tensor memory
   uint64_t* dv_done = s_full + 5;               // dV MMAs of a step complete: the P^T columns may be overwritten
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+  uint64_t* dk_done = s_full + 6;               // dK MMAs of a step complete (with dq_full: dS^T buffer may be overwritten)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 7);
 
   if ((smem_u32(smem) & 1023u) != 0) return;
 
@@ -197,10 +209,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmDQ);
     mbar_init(kv_full, 1);
     for (int s = 0; s < AB_STAGES; ++s) {
       mbar_init(&qdo_full[s], 1 + 32);  // expect_tx arrive + one arrive per staging lane
-      mbar_init(&qdo_empty[s], 2);      // released by the dV issuer and by the dK/dQ issuer
+      mbar_init(&qdo_empty[s], 2);      // released by the dV issuer (dO_i) and by the dK issuer (Q_i)
     }
     mbar_init(s_full, 1);
     mbar_init(pds_ready, AB_CWARPS);
@@ -208,6 +221,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(dq_empty, AB_CWARPS);
     mbar_init(sdp_free, AB_CWARPS);
     mbar_init(dv_done, 1);
+    mbar_init(dk_done, 1);
     fence_barrier_init();
   }
   if (warp == AB_W_MMA_S) {
@@ -253,30 +267,51 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (++st == AB_STAGES) st = 0;
     }
   } else if (warp == AB_W_MMA_S) {
-    // ------------------------------------------------------------ MMA issuer 1: S^T = K Q^T and dP^T = V dO^T.
-    // Three issuing warps keep the issue rate above the 32..64-cycle MMAs; S^T / dP^T of step it+1 only wait for the
-    // previous tiles to be READ out of tensor memory (sdp_free), not for the math on them.
+    // ------------------------------------------------------------ MMA issuer 1: S^T = K Q^T, dP^T = V dO^T, dQ = dS K.
+    // S^T / dP^T of step it+1 only wait for step it's tiles to be READ out of tensor memory (sdp_free, early in the
+    // step); dQ of step it waits for its dS^T (pds_ready, late in the step) and for the previous dQ to have left tensor
+    // memory (dq_empty) — the two jobs never compete for this thread.  dQ: A = the dS^T buffer read MN-major (M =
+    // queries, 64 per block, blocks AB_TILE apart), B = K MN-major.
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // K-major x K-major, N = 128 queries
+      constexpr uint32_t idesc_nn = make_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major (dQ)
       mbar_wait(kv_full, 0);
       // descriptors are built once; per K-step only the 14-bit start-address field advances (tight issue loop)
       const uint64_t k_desc = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t v_desc = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
       const uint64_t q_desc0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t do_desc0 = make_smem_desc_sw128(smem_u32(sDO), 16, 1024);
+      const uint64_t k_desc_mn = make_smem_desc_sw128(smem_u32(sK), AB_TILE, 1024);
+      const uint64_t ds_desc_mn = make_smem_desc_sw128(smem_u32(sDS), AB_TILE, 1024);
       int st = 0;
-      for (int it = 0; it < n_it; ++it) {
-        const uint64_t q_desc = q_desc0 + st * (AB_TILE >> 4), do_desc = do_desc0 + st * (AB_TILE >> 4);
-        mbar_wait(&qdo_full[st], (it / AB_STAGES) & 1);
-        if (it > 0) mbar_wait(sdp_free, (it - 1) & 1);
-        tc_fence_after();
+      for (int it = 0; it <= n_it; ++it) {
+        if (it < n_it) {  // S^T / dP^T of step `it`
+          const uint64_t q_desc = q_desc0 + st * (AB_TILE >> 4), do_desc = do_desc0 + st * (AB_TILE >> 4);
+          mbar_wait(&qdo_full[st], (it / AB_STAGES) & 1);
+          AB_TR(64 + (it - 6) * 4 + 0);
+          if (it > 0) mbar_wait(sdp_free, (it - 1) & 1);
+          AB_TR(64 + (it - 6) * 4 + 1);
+          tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < AB_HD / 16; ++k) {
-          umma_ss(tS, k_desc + k * 2, q_desc + k * 2, idesc_s, k > 0 ? 1u : 0u);
-          umma_ss(tDP, v_desc + k * 2, do_desc + k * 2, idesc_s, k > 0 ? 1u : 0u);
+          for (int k = 0; k < AB_HD / 16; ++k) {
+            umma_ss(tS, k_desc + k * 2, q_desc + k * 2, idesc_s, k > 0 ? 1u : 0u);
+            umma_ss(tDP, v_desc + k * 2, do_desc + k * 2, idesc_s, k > 0 ? 1u : 0u);
+          }
+          umma_commit(s_full);
+          AB_TR(64 + (it - 6) * 4 + 2);
+          if (++st == AB_STAGES) st = 0;
         }
-        umma_commit(s_full);
-        if (++st == AB_STAGES) st = 0;
+        if (it > 0) {  // dQ of step it-1
+          const int pit = it - 1;
+          mbar_wait(pds_ready, pit & 1);
+          if (pit > 0) mbar_wait(dq_empty, (pit - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < AB_T / 16; ++k)
+            umma_ss(tDQ, ds_desc_mn + k * (2048 >> 4), k_desc_mn + k * (2048 >> 4), idesc_nn, k > 0 ? 1u : 0u);
+          umma_commit(dq_full);
+          AB_TR(64 + (it - 6) * 4 + 3);
+        }
       }
     }
   } else if (warp == AB_W_MMA_DV) {
@@ -288,41 +323,36 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       for (int it = 0; it < n_it; ++it) {
         const uint64_t do_desc = do_desc0 + st * (AB_TILE >> 4);
         mbar_wait(pds_ready, it & 1);
+        AB_TR(96 + (it - 6) * 4 + 0);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < AB_T / 16; ++k)
           umma_ts(tDV, tP + k * 8, do_desc + k * (2048 >> 4), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(dv_done);
         umma_commit(&qdo_empty[st]);
+        AB_TR(96 + (it - 6) * 4 + 1);
         if (++st == AB_STAGES) st = 0;
       }
     }
-  } else if (warp == AB_W_MMA_DKQ) {
-    // ------------------------------------------------------------ MMA issuer 3: dK += dS^T Q ; dQ = dS K
+  } else if (warp == AB_W_MMA_DK) {
+    // ------------------------------------------------------------ MMA issuer 3: dK += dS^T Q
     if (lane == 0) {
       constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);   // A K-major, B MN-major, N = 64
-      constexpr uint32_t idesc_nn = make_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major (dQ)
-      mbar_wait(kv_full, 0);
-      const uint64_t k_desc_mn = make_smem_desc_sw128(smem_u32(sK), AB_TILE, 1024);
-      const uint64_t ds_desc_k = make_smem_desc_sw128(smem_u32(sDS), 16, 1024);        // K-major view (dK)
-      const uint64_t ds_desc_mn = make_smem_desc_sw128(smem_u32(sDS), AB_TILE, 1024);  // MN-major view (dQ)
+      const uint64_t ds_desc_k = make_smem_desc_sw128(smem_u32(sDS), 16, 1024);        // K-major view of dS^T
       const uint64_t q_desc0 = make_smem_desc_sw128(smem_u32(sQ), AB_TILE, 1024);
       int st = 0;
       for (int it = 0; it < n_it; ++it) {
         const uint64_t q_desc = q_desc0 + st * (AB_TILE >> 4);
         mbar_wait(pds_ready, it & 1);
-        if (it > 0) mbar_wait(dq_empty, (it - 1) & 1);
+        AB_TR(128 + (it - 6) * 4 + 0);
         tc_fence_after();
-        // dK and dQ interleaved.  dQ: A = dS^T buffer read MN-major (M = queries, 64 per block, blocks AB_TILE apart),
-        // B = K MN-major
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k) {
+        for (int k = 0; k < AB_T / 16; ++k)
           umma_ss(tDK, ds_desc_k + ((k >> 2) * AB_TILE + (k & 3) * 32) / 16, q_desc + k * (2048 >> 4), idesc_kn,
                   (it > 0 || k > 0) ? 1u : 0u);
-          umma_ss(tDQ, ds_desc_mn + k * (2048 >> 4), k_desc_mn + k * (2048 >> 4), idesc_nn, k > 0 ? 1u : 0u);
-        }
         umma_commit(&qdo_empty[st]);
-        umma_commit(dq_full);
+        umma_commit(dk_done);
+        AB_TR(128 + (it - 6) * 4 + 1);
         if (++st == AB_STAGES) st = 0;
       }
     }
@@ -334,26 +364,54 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int kj = j * AB_T + r;             // key position
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
 
-    auto dq_flush = [&](int i_tile) {  // dQ of query tile i_tile: lane r now means QUERY row r; 16 head-dim cols/thread
-      float* dst = dq_acc + (seq0 + i_tile * AB_T + r) * d + h * AB_HD + cq * 16;
-      const bool dq_ok = i_tile * AB_T + r < T;
+    // dQ of query tile i_tile leaves through a TMA reduce-add: lane r now means QUERY row r, 16 head-dim columns per
+    // thread.  The four warps of a lane quarter stage their [32 rows x 64] fp32 block (two 128B-swizzled column halves)
+    // and one of their threads issues the two bulk reduce-adds into dq_acc — no per-lane strided red.global traffic on
+    // the compute warps, and tensor memory is released (dq_empty) as soon as the values are in registers.
+    // Rows beyond T hold exact zeros (P is masked to 0 there), so adding them is harmless.
+    uint8_t* dq_blk = sDQ + quarter * (AB_DQ_STAGE / 4);
+    const bool dq_elected = (cq == 0 && lane == 0);
+    auto dq_flush = [&](int i_tile, bool release) {
       uint32_t t[16];
       tmem_ld16(tDQ + lane_off + cq * 16, t);
       tmem_ld_wait();
-      if (dq_ok) {
+      if (release) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_empty);
+      }
+      if (dq_elected) bulk_wait_group_read<0>();  // the previous reduce-add has finished reading the staging block
+      named_bar_sync(1 + quarter, 128);
+      uint8_t* row = dq_blk + (cq >> 1) * 4096 + lane * 128;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          red_add_f32x4(dst + q4 * 4, __uint_as_float(t[4 * q4]), __uint_as_float(t[4 * q4 + 1]),
-                        __uint_as_float(t[4 * q4 + 2]), __uint_as_float(t[4 * q4 + 3]));
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(row + ((((cq & 1) * 4 + c) ^ (lane & 7)) << 4)) =
+            make_uint4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
+      fence_proxy_async_smem();
+      named_bar_sync(1 + quarter, 128);
+      if (dq_elected) {
+        const int row0 = static_cast<int>(seq0 + i_tile * AB_T + quarter * 32);
+        tma_reduce_add_2d(&tmDQ, dq_blk, h * AB_HD, row0);
+        tma_reduce_add_2d(&tmDQ, dq_blk + 4096, h * AB_HD + 32, row0);
+        bulk_commit_group();
       }
     };
 
     int st = 0;
     for (int it = 0; it < n_it; ++it) {
       const int i = j + it;
+      const bool trw = tr_on && (warp == 0 || warp == 15);
+      const int trb = (warp == 0 ? 0 : 160) + (it - 6) * 8;
+#define AB_TRC(k_)                                                                \
+  do {                                                                            \
+    if (trw && it >= 6 && it < 10 && lane == 0) g_dbg_counters[trb + (k_)] = clock64(); \
+  } while (0)
+      AB_TRC(0);
       // one hand-off in: tiles of this step are in tensor memory (s_full), its vectors are staged (qdo_full)
       mbar_wait(&qdo_full[st], (it / AB_STAGES) & 1);
+      AB_TRC(1);
       mbar_wait(s_full, it & 1);
+      AB_TRC(2);
       tc_fence_after();
       const float* lse2 = sLse + st * AB_T + cq * 32;
       const float* dl = sDelta + st * AB_T + cq * 32;
@@ -365,6 +423,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tmem_ld32(tS + lane_off + cq * 32, ts);
       tmem_ld32(tDP + lane_off + cq * 32, tdp);
       tmem_ld_wait();
+      AB_TRC(3);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_free);  // S^T / dP^T of the next step may be issued while we do the math
@@ -393,12 +452,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         p[4 * q4 + 2] = r1.x;
         p[4 * q4 + 3] = r1.y;
       }
-      // the previous step's dV MMAs must be done with the P^T columns, its dK/dQ MMAs with the dS^T buffer
+      AB_TRC(4);
+      // the previous step's dV MMAs must be done with the P^T columns, its dK and dQ MMAs with the dS^T buffer
       if (it > 0) {
         mbar_wait(dv_done, (it - 1) & 1);
+        mbar_wait(dk_done, (it - 1) & 1);
         mbar_wait(dq_full, (it - 1) & 1);
         tc_fence_after();
       }
+      AB_TRC(5);
       tmem_st16(tP + lane_off + cq * 16, w);
       store_bf16_row32(sDS + (cq >> 1) * AB_TILE + r * 128, r, (cq & 1) * 4, p);
       tmem_st_wait();
@@ -406,22 +468,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_ready);  // one hand-off out
+      AB_TRC(6);
+      if (tr_on && it >= 6 && it < 10 && lane == 0) g_dbg_counters[192 + (it - 6) * 16 + warp] = clock64();
 
-      // dQ of the previous step (the red.adds drain while the tensor pipe runs dV / dK of this step)
-      if (it > 0) {
-        dq_flush(i - 1);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dq_empty);
-      }
+      // dQ of the previous step: out of tensor memory first (unblocks this step's dQ MMAs), then off to dq_acc
+      if (it > 0) dq_flush(i - 1, true);
+      AB_TRC(7);
       if (++st == AB_STAGES) st = 0;
     }
 
     // ---- tail: dQ of the last step, then dV / dK of this key tile (16 head-dim columns per thread)
     mbar_wait(dq_full, (n_it - 1) & 1);
     mbar_wait(dv_done, (n_it - 1) & 1);
+    mbar_wait(dk_done, (n_it - 1) & 1);
     tc_fence_after();
-    dq_flush(j + n_it - 1);
+    dq_flush(j + n_it - 1, false);
     const bool k_ok = kj < T;
     {
       uint32_t t[16];
@@ -475,6 +536,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   }
 
+  if (warp < AB_CWARPS && (warp >> 2) == 0 && lane == 0) bulk_wait_group<0>();  // dQ reduce-adds have landed
   tc_fence_before();
   __syncthreads();
   if (warp == AB_W_MMA_S) {
@@ -486,11 +548,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 }  // namespace plm
 
 extern "C" int plm_debug_counters(unsigned long long* out, int32_t n, int32_t reset) {
-  if (!out || n <= 0 || n > 32) return plm::fail(PLM_ERR_INVALID, "debug_counters: bad argument");
+  if (!out || n <= 0 || n > 256) return plm::fail(PLM_ERR_INVALID, "debug_counters: bad argument");
   cudaError_t e = cudaMemcpyFromSymbol(out, plm::g_dbg_counters, sizeof(unsigned long long) * n);
   if (e != cudaSuccess) return plm::fail(PLM_ERR_CUDA, "debug_counters: %s", cudaGetErrorString(e));
   if (reset) {
-    unsigned long long zeros[32] = {0};
+    unsigned long long zeros[256] = {0};
     e = cudaMemcpyToSymbol(plm::g_dbg_counters, zeros, sizeof(zeros));
     if (e != cudaSuccess) return plm::fail(PLM_ERR_CUDA, "debug_counters reset: %s", cudaGetErrorString(e));
   }
@@ -525,6 +587,9 @@ extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, 
   if (rc != PLM_OK) return rc;
   rc = make_tmap_bf16_2d(&tmDO, dout, rows, d, d, AB_T, 64);
   if (rc != PLM_OK) return rc;
+  CUtensorMap tmDQ;  // dq_acc fp32 [rows, d]: boxes of 32 rows x 32 columns for the reduce-adds
+  rc = make_tmap_f32_2d(&tmDQ, dq_acc, rows, d, d, 32, 32);
+  if (rc != PLM_OK) return rc;
 
   cudaError_t e = cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * d * sizeof(float), stream);
   if (e != cudaSuccess) return fail(PLM_ERR_CUDA, "attn_bwd memset: %s", cudaGetErrorString(e));
@@ -538,9 +603,9 @@ extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, 
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   dim3 grid((T + AB_T - 1) / AB_T, H, B);
-  attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, lse, delta, seg_start, rope_table,
+  attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, seg_start, rope_table,
                                                          static_cast<__nv_bfloat16*>(dqkv), dq_acc, T, H, scale,
-                                                         scale * 1.4426950408889634f);
+                                                         scale * 1.4426950408889634f, getenv("PLM_ATTN_TRACE") ? 1 : 0);
   rc = check_launch("attn_bwd");
   if (rc != PLM_OK) return rc;
   {

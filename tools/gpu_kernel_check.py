@@ -570,6 +570,56 @@ def case_bw_perf():
   return out
 
 
+def case_attn_bwd_trace():
+  """clock64 timeline of one attention-backward CTA (PLM_ATTN_TRACE): where a steady-state step spends its cycles."""
+  import ctypes
+  import torch
+  from plainlm_b200 import ops, _lib
+
+  dev = 'cuda'
+  B, T, H, hd = 8, 2048, 16, 64
+  d = H * hd
+  qkv = torch.randn(B * T, 3 * d, device=dev).to(torch.bfloat16)
+  out = torch.empty(B * T, d, device=dev, dtype=torch.bfloat16)
+  lse = torch.empty(B, H, T, device=dev)
+  dout = torch.randn(B * T, d, device=dev).to(torch.bfloat16)
+  dqkv = torch.empty(B * T, 3 * d, device=dev, dtype=torch.bfloat16)
+  delta = torch.empty(B, H, T, device=dev)
+  dq_acc = torch.empty(B * T, d, device=dev)
+  ops.attn_fwd(qkv, out, lse, B, T, H, hd)
+  for _ in range(2):
+    ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd)
+  os.environ['PLM_ATTN_TRACE'] = '1'
+  ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd)
+  os.environ.pop('PLM_ATTN_TRACE')
+  torch.cuda.synchronize()
+  buf = (ctypes.c_ulonglong * 256)()
+  _lib.check(_lib.load().plm_debug_counters(buf, 256, 1), 'plm_debug_counters')
+  v = list(buf)
+  t0 = v[0]
+  ev = []
+  names = {0: 'C0', 160: 'C15', 64: 'iS', 96: 'iDV', 128: 'iDK'}
+  labels = {
+    'C0': ['top', 'qdo_full', 's_full', 'tmem_ld done', 'math done', 'dv_done/dq_full', 'pds_ready sent', 'dq flushed'],
+    'C15': ['top', 'qdo_full', 's_full', 'tmem_ld done', 'math done', 'dv_done/dq_full', 'pds_ready sent', 'dq flushed'],
+    'iS': ['qdo_full', 'sdp_free', 'S/dP issued', 'dQ(it-1) issued'], 'iDV': ['pds_ready', 'dV issued', '-', '-'],
+    'iDK': ['pds_ready', 'dK issued', '-', '-'],
+  }
+  for base, nm in names.items():
+    per = 8 if nm.startswith('C') else 4
+    for itr in range(4):
+      for k in range(per):
+        t = v[base + itr * per + k]
+        if t:
+          ev.append((t - t0, f'{nm} it{6 + itr} {labels[nm][k]}'))
+  for itr in range(4):
+    ws = [v[192 + itr * 16 + w] - t0 for w in range(16) if v[192 + itr * 16 + w]]
+    if ws:
+      ev.append((max(ws), f'ALL it{6 + itr} pds_ready sent by the last warp (first {min(ws)})'))
+  ev.sort()
+  return [{'case': 'timeline', 'events': [f'{t:7d} {n}' for t, n in ev]}]
+
+
 def case_attn_perf():
   import torch
   from plainlm_b200 import ops
@@ -646,6 +696,7 @@ CASES['attn_perf'] = case_attn_perf
 CASES['bw_perf'] = case_bw_perf
 CASES['gemm_epi_perf'] = case_gemm_epi_perf
 CASES['gemm_feed_probe'] = case_gemm_feed_probe
+CASES['attn_bwd_trace'] = case_attn_bwd_trace
 CASES['gemm_sustained'] = case_gemm_sustained
 
 
