@@ -33,8 +33,8 @@ constexpr int AB_STAGES = 3;       // Q_i / dO_i ring
 constexpr int AB_TILE = AB_T * AB_HD * 2;  // 16 KB
 // K, V, (Q,dO) x AB_STAGES, dS^T (2 blocks), dQ staging (fp32 128 x 64), vectors (lse2, delta, seg) x stages, barriers
 constexpr int AB_VEC_BYTES = AB_STAGES * 3 * AB_T * 4;
-constexpr int AB_DQ_STAGE = AB_T * AB_HD * 4;  // 32 KB: per lane quarter 2 column halves of [32 rows x 128 B], swizzled
-constexpr int AB_SMEM = AB_TILE * (2 + 2 * AB_STAGES + 2) + AB_DQ_STAGE + AB_VEC_BYTES + 256;
+constexpr int AB_DQ_STAGE = AB_T * AB_HD * 4;  // 32 KB: per compute warp [32 rows x 64 B] (64-byte swizzle)
+constexpr int AB_SMEM = AB_TILE * (2 + 2 * AB_STAGES + 2) + AB_DQ_STAGE + AB_VEC_BYTES + 512;
 
 __device__ __forceinline__ float ex2b(float x) {
   float y;
@@ -178,13 +178,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* qdo_full = bars + 1;                // [AB_STAGES]  TMA bytes of Q_i, dO_i + the 32 staging lanes
   uint64_t* qdo_empty = bars + 1 + AB_STAGES;   // [AB_STAGES]
   uint64_t* s_full = bars + 1 + 2 * AB_STAGES;  // S^T and dP^T of a step are in tensor memory
-  uint64_t* pds_ready = s_full + 1;             // P^T (tensor memory) and dS^T (smem) of a step are written
-  uint64_t* dq_full = s_full + 2;               // dQ MMAs of a step complete
-  uint64_t* dq_empty = s_full + 3;              // dQ of a step has been read out of tensor memory
-  uint64_t* sdp_free = s_full + 4;              // compute warps have read S^T and dP^T out of tensor memory
-  uint64_t* dv_done = s_full + 5;               // dV MMAs of a step complete: the P^T columns may be overwritten
-  uint64_t* dk_done = s_full + 6;               // dK MMAs of a step complete (with dq_full: dS^T buffer may be overwritten)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 7);
+  uint64_t* dq_full = s_full + 1;               // dQ MMAs of a step complete
+  uint64_t* dq_empty = s_full + 2;              // dQ of a step has been read out of tensor memory
+  uint64_t* sdp_free = s_full + 3;              // compute warps have read S^T and dP^T out of tensor memory
+  // Fine-grained hand-offs, so that the four warps sharing a scheduler can drift apart and overlap their TMEM / MUFU /
+  // store phases instead of meeting at one CTA-wide barrier per step:
+  uint64_t* pds_cq = s_full + 4;    // [4] query-column quarter cq: P^T cols / dS^T cols of all 128 keys written
+                                    //     (the K-chunks 2cq, 2cq+1 of the dV and dK GEMMs)
+  uint64_t* pds_q = s_full + 8;     // [4] key-row quarter q: dS^T rows written for all queries (K-chunks 2q, 2q+1 of dQ)
+  uint64_t* free_v = s_full + 12;   // [4] dV K-chunks of cq complete: P^T columns of cq may be overwritten
+  uint64_t* free_k = s_full + 16;   // [4] dK K-chunks of cq complete   } together: the dS^T block of warp (q, cq)
+  uint64_t* free_q = s_full + 20;   // [4] dQ K-chunks of q complete    } may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 24);
 
   if ((smem_u32(smem) & 1023u) != 0) return;
 
@@ -216,12 +221,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       mbar_init(&qdo_empty[s], 2);      // released by the dV issuer (dO_i) and by the dK issuer (Q_i)
     }
     mbar_init(s_full, 1);
-    mbar_init(pds_ready, AB_CWARPS);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, AB_CWARPS);
     mbar_init(sdp_free, AB_CWARPS);
-    mbar_init(dv_done, 1);
-    mbar_init(dk_done, 1);
+    for (int g = 0; g < 4; ++g) {
+      mbar_init(&pds_cq[g], 4);
+      mbar_init(&pds_q[g], 4);
+      mbar_init(&free_v[g], 1);
+      mbar_init(&free_k[g], 1);
+      mbar_init(&free_q[g], 1);
+    }
     fence_barrier_init();
   }
   if (warp == AB_W_MMA_S) {
@@ -303,12 +312,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
         if (it > 0) {  // dQ of step it-1
           const int pit = it - 1;
-          mbar_wait(pds_ready, pit & 1);
           if (pit > 0) mbar_wait(dq_empty, (pit - 1) & 1);
-          tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < AB_T / 16; ++k)
+          for (int k = 0; k < AB_T / 16; ++k) {
+            if ((k & 1) == 0) {  // K-chunk k = key rows [16k, 16k+16): written by the warps of lane quarter k/2
+              mbar_wait(&pds_q[k >> 1], pit & 1);
+              tc_fence_after();
+            }
             umma_ss(tDQ, ds_desc_mn + k * (2048 >> 4), k_desc_mn + k * (2048 >> 4), idesc_nn, k > 0 ? 1u : 0u);
+            if (k & 1) umma_commit(&free_q[k >> 1]);
+          }
           umma_commit(dq_full);
           AB_TR(64 + (it - 6) * 4 + 3);
         }
@@ -322,13 +335,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       int st = 0;
       for (int it = 0; it < n_it; ++it) {
         const uint64_t do_desc = do_desc0 + st * (AB_TILE >> 4);
-        mbar_wait(pds_ready, it & 1);
-        AB_TR(96 + (it - 6) * 4 + 0);
-        tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k)
+        for (int k = 0; k < AB_T / 16; ++k) {
+          if ((k & 1) == 0) {  // K-chunk k = queries [16k, 16k+16): P^T columns written by the warps of column quarter k/2
+            mbar_wait(&pds_cq[k >> 1], it & 1);
+            if (k == 0) AB_TR(96 + (it - 6) * 4 + 0);
+            tc_fence_after();
+          }
           umma_ts(tDV, tP + k * 8, do_desc + k * (2048 >> 4), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(dv_done);
+          if (k & 1) umma_commit(&free_v[k >> 1]);
+        }
         umma_commit(&qdo_empty[st]);
         AB_TR(96 + (it - 6) * 4 + 1);
         if (++st == AB_STAGES) st = 0;
@@ -343,15 +359,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       int st = 0;
       for (int it = 0; it < n_it; ++it) {
         const uint64_t q_desc = q_desc0 + st * (AB_TILE >> 4);
-        mbar_wait(pds_ready, it & 1);
-        AB_TR(128 + (it - 6) * 4 + 0);
-        tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k)
+        for (int k = 0; k < AB_T / 16; ++k) {
+          if ((k & 1) == 0) {
+            mbar_wait(&pds_cq[k >> 1], it & 1);
+            if (k == 0) AB_TR(128 + (it - 6) * 4 + 0);
+            tc_fence_after();
+          }
           umma_ss(tDK, ds_desc_k + ((k >> 2) * AB_TILE + (k & 3) * 32) / 16, q_desc + k * (2048 >> 4), idesc_kn,
                   (it > 0 || k > 0) ? 1u : 0u);
+          if (k & 1) umma_commit(&free_k[k >> 1]);
+        }
         umma_commit(&qdo_empty[st]);
-        umma_commit(dk_done);
         AB_TR(128 + (it - 6) * 4 + 1);
         if (++st == AB_STAGES) st = 0;
       }
@@ -364,13 +383,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     const int kj = j * AB_T + r;             // key position
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
 
-    // dQ of query tile i_tile leaves through a TMA reduce-add: lane r now means QUERY row r, 16 head-dim columns per
-    // thread.  The four warps of a lane quarter stage their [32 rows x 64] fp32 block (two 128B-swizzled column halves)
-    // and one of their threads issues the two bulk reduce-adds into dq_acc — no per-lane strided red.global traffic on
-    // the compute warps, and tensor memory is released (dq_empty) as soon as the values are in registers.
-    // Rows beyond T hold exact zeros (P is masked to 0 there), so adding them is harmless.
-    uint8_t* dq_blk = sDQ + quarter * (AB_DQ_STAGE / 4);
-    const bool dq_elected = (cq == 0 && lane == 0);
+    // dQ of query tile i_tile leaves through TMA reduce-adds: lane r now means QUERY row r, 16 head-dim columns per
+    // thread.  Each warp stages its own [32 rows x 16] fp32 block (64-byte swizzle) and issues one bulk reduce-add into
+    // dq_acc — no strided red.global traffic, no cross-warp synchronisation, and tensor memory is released (dq_empty)
+    // as soon as the values are in registers.  Rows beyond T hold exact zeros (P is masked to 0 there).
+    uint8_t* dq_blk = sDQ + warp * (AB_DQ_STAGE / AB_CWARPS);
     auto dq_flush = [&](int i_tile, bool release) {
       uint32_t t[16];
       tmem_ld16(tDQ + lane_off + cq * 16, t);
@@ -380,19 +397,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_empty);
       }
-      if (dq_elected) bulk_wait_group_read<0>();  // the previous reduce-add has finished reading the staging block
-      named_bar_sync(1 + quarter, 128);
-      uint8_t* row = dq_blk + (cq >> 1) * 4096 + lane * 128;
+      if (lane == 0) bulk_wait_group_read<0>();  // this warp's previous reduce-add has finished reading the block
+      __syncwarp();
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(row + ((((cq & 1) * 4 + c) ^ (lane & 7)) << 4)) =
+        *reinterpret_cast<uint4*>(dq_blk + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
             make_uint4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
       fence_proxy_async_smem();
-      named_bar_sync(1 + quarter, 128);
-      if (dq_elected) {
-        const int row0 = static_cast<int>(seq0 + i_tile * AB_T + quarter * 32);
-        tma_reduce_add_2d(&tmDQ, dq_blk, h * AB_HD, row0);
-        tma_reduce_add_2d(&tmDQ, dq_blk + 4096, h * AB_HD + 32, row0);
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(&tmDQ, dq_blk, h * AB_HD + cq * 16, static_cast<int>(seq0 + i_tile * AB_T + quarter * 32));
         bulk_commit_group();
       }
     };
@@ -453,11 +467,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         p[4 * q4 + 3] = r1.y;
       }
       AB_TRC(4);
-      // the previous step's dV MMAs must be done with the P^T columns, its dK and dQ MMAs with the dS^T buffer
+      // the previous step's dV MMAs must be done with this warp's P^T columns, its dK / dQ MMAs with its dS^T block
       if (it > 0) {
-        mbar_wait(dv_done, (it - 1) & 1);
-        mbar_wait(dk_done, (it - 1) & 1);
-        mbar_wait(dq_full, (it - 1) & 1);
+        mbar_wait(&free_v[cq], (it - 1) & 1);
+        mbar_wait(&free_k[cq], (it - 1) & 1);
+        mbar_wait(&free_q[quarter], (it - 1) & 1);
         tc_fence_after();
       }
       AB_TRC(5);
@@ -467,20 +481,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_ready);  // one hand-off out
+      if (lane == 0) {  // hand-off out
+        mbar_arrive(&pds_cq[cq]);
+        mbar_arrive(&pds_q[quarter]);
+      }
       AB_TRC(6);
       if (tr_on && it >= 6 && it < 10 && lane == 0) g_dbg_counters[192 + (it - 6) * 16 + warp] = clock64();
 
       // dQ of the previous step: out of tensor memory first (unblocks this step's dQ MMAs), then off to dq_acc
-      if (it > 0) dq_flush(i - 1, true);
+      if (it > 0) {
+        mbar_wait(dq_full, (it - 1) & 1);
+        tc_fence_after();
+        dq_flush(i - 1, true);
+      }
       AB_TRC(7);
       if (++st == AB_STAGES) st = 0;
     }
 
     // ---- tail: dQ of the last step, then dV / dK of this key tile (16 head-dim columns per thread)
     mbar_wait(dq_full, (n_it - 1) & 1);
-    mbar_wait(dv_done, (n_it - 1) & 1);
-    mbar_wait(dk_done, (n_it - 1) & 1);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {  // every K-chunk of the last dV / dK GEMMs
+      mbar_wait(&free_v[g], (n_it - 1) & 1);
+      mbar_wait(&free_k[g], (n_it - 1) & 1);
+    }
     tc_fence_after();
     dq_flush(j + n_it - 1, false);
     const bool k_ok = kj < T;
@@ -536,7 +560,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   }
 
-  if (warp < AB_CWARPS && (warp >> 2) == 0 && lane == 0) bulk_wait_group<0>();  // dQ reduce-adds have landed
+  if (warp < AB_CWARPS && lane == 0) bulk_wait_group<0>();  // dQ reduce-adds have landed
   tc_fence_before();
   __syncthreads();
   if (warp == AB_W_MMA_S) {
@@ -587,8 +611,8 @@ extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, 
   if (rc != PLM_OK) return rc;
   rc = make_tmap_bf16_2d(&tmDO, dout, rows, d, d, AB_T, 64);
   if (rc != PLM_OK) return rc;
-  CUtensorMap tmDQ;  // dq_acc fp32 [rows, d]: boxes of 32 rows x 32 columns for the reduce-adds
-  rc = make_tmap_f32_2d(&tmDQ, dq_acc, rows, d, d, 32, 32);
+  CUtensorMap tmDQ;  // dq_acc fp32 [rows, d]: boxes of 32 rows x 16 columns (one compute warp's share) for the reduce-adds
+  rc = make_tmap_f32_2d(&tmDQ, dq_acc, rows, d, d, 32, 16);
   if (rc != PLM_OK) return rc;
 
   cudaError_t e = cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * d * sizeof(float), stream);

@@ -108,15 +108,16 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(PLM_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   if (!aligned16(base) || (ld % 4) != 0) return fail(PLM_ERR_INVALID, "tensor map: base/ld not 16-byte aligned");
-  if (box_cols * 4 != 128 || box_rows == 0 || box_rows > 256)
+  if ((box_cols * 4 != 128 && box_cols * 4 != 64) || box_rows == 0 || box_rows > 256)
     return fail(PLM_ERR_INVALID, "tensor map: bad fp32 box %ux%u", box_rows, box_cols);
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {ld * 4};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estride[2] = {1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estride,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  box_cols * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(PLM_ERR_CUDA, "cuTensorMapEncodeTiled(f32) failed (%d) rows=%llu cols=%llu ld=%llu", (int)r,
                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);

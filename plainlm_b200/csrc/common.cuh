@@ -26,7 +26,7 @@ int ensure_context(const void* device_ptr);
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols);
 
-// Same for an fp32 tensor (box_cols * 4 bytes must be 128).
+// Same for an fp32 tensor: box_cols * 4 bytes must be 128 (128-byte swizzle) or 64 (64-byte swizzle).
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                      uint32_t box_cols);
 
