@@ -1,18 +1,22 @@
 // Flash-attention backward on tcgen05 (backward of models/transformer.py:53-63, reached from engine/engine.py:120).
 //
-// One CTA per (128-key tile j, head, batch), looping over the query tiles i >= j that can see it. 640 threads:
-//   warps 0..15 compute: warp = (TMEM lane quarter, column quarter); a thread owns 32 columns of key row r of the
-//               transposed score tile — four warps per scheduler so TMEM / smem / MUFU latencies overlap
-//   warps 16-18 MMA issuers (S^T,dP^T | dV | dK,dQ: one thread each)   warp 19 TMA producer (K,V; Q_i,dO_i 3-stage ring)
+// One CTA per (128-key tile j, head, batch), looping over the query tiles i >= j that can see it. 768 threads:
+//   warps 0..15  compute: warp = (TMEM lane quarter, column quarter); a thread owns 32 columns of key row r of the
+//                transposed score tile — four warps per scheduler so TMEM / smem / MUFU latencies overlap
+//   warps 16-18  MMA issuers (S^T,dP^T,dQ | dV | dK: one thread each)   warp 19 TMA producer (K,V; Q_i,dO_i 3-stage ring)
+//   warps 20-23  dQ drain (one per TMEM lane quarter): tensor memory -> swizzled smem -> TMA bulk reduce-add into dq_acc
+// 768 threads leave 80 registers per thread; setmaxnreg moves registers from warps 16-23 (48) to the compute warps (96).
 // Five GEMMs per (j, i) pair, all on the tensor core, all 512 TMEM columns in use:
 //   S^T  = K Q_i^T        (cols   0..127)      dP^T = V dO_i^T       (cols 128..255)
 //   dV  += P^T dO_i       (cols 256..319)      dK  += dS^T Q_i       (cols 320..383)
-//   dQ_i = dS K           (cols 384..447) -> fp32 red.add into dq_acc (finalised by dq_finalize_kernel)
+//   dQ_i = dS K           (cols 384..447) -> fp32 reduce-add into dq_acc (finalised by dq_finalize_kernel)
 //   P^T as packed bf16    (cols 448..511) -> A operand of the dV GEMM read straight from tensor memory
 // dS^T is written once to swizzled smem as a K-major A operand (dK) and re-read MN-major for the dQ GEMM; Q_i / dO_i /
 // K are consumed as MN-major B operands straight from their TMA boxes — no transposes anywhere.  S^T / dP^T of step
 // i+1 are issued as soon as the compute warps have READ step i's tiles out of tensor memory, so the tensor pipe works
 // on the neighbouring step while the exp / dS math runs.  dK and dQ are rotated back through RoPE in the epilogues.
+// Measured (PLM_ATTN_TRACE timeline, tools/gpu_kernel_check.py --case attn_bwd_trace): a step takes ~3000 cycles, of
+// which ~1500 are the exp/dS math (MUFU-bound: 16384 ex2 per step at 16/clk/SM = 1024) and the rest hand-off latency.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -28,12 +32,15 @@ constexpr int AB_W_MMA_S = AB_CWARPS;       // issues S^T, dP^T (early in a step
 constexpr int AB_W_MMA_DV = AB_CWARPS + 1;  // issues dV
 constexpr int AB_W_MMA_DK = AB_CWARPS + 2;  // issues dK
 constexpr int AB_W_TMA = AB_CWARPS + 3;     // TMA producer
-constexpr int AB_THREADS = (AB_CWARPS + 4) * 32;
+constexpr int AB_W_DRAIN = AB_CWARPS + 4;   // four dQ drain warps, one per TMEM lane quarter
+constexpr int AB_THREADS = (AB_CWARPS + 8) * 32;
+constexpr int AB_REGS_COMPUTE = 96;  // setmaxnreg: compute warpgroups take registers from the auxiliary ones
+constexpr int AB_REGS_AUX = 48;
 constexpr int AB_STAGES = 3;       // Q_i / dO_i ring
 constexpr int AB_TILE = AB_T * AB_HD * 2;  // 16 KB
 // K, V, (Q,dO) x AB_STAGES, dS^T (2 blocks), dQ staging (fp32 128 x 64), vectors (lse2, delta, seg) x stages, barriers
 constexpr int AB_VEC_BYTES = AB_STAGES * 3 * AB_T * 4;
-constexpr int AB_DQ_STAGE = AB_T * AB_HD * 4;  // 32 KB: per compute warp [32 rows x 64 B] (64-byte swizzle)
+constexpr int AB_DQ_STAGE = AB_T * AB_HD * 4;  // 32 KB: per lane quarter two [32 rows x 128 B] blocks (128-byte swizzle)
 constexpr int AB_SMEM = AB_TILE * (2 + 2 * AB_STAGES + 2) + AB_DQ_STAGE + AB_VEC_BYTES + 512;
 
 __device__ __forceinline__ float ex2b(float x) {
@@ -181,15 +188,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* dq_full = s_full + 1;               // dQ MMAs of a step complete
   uint64_t* dq_empty = s_full + 2;              // dQ of a step has been read out of tensor memory
   uint64_t* sdp_free = s_full + 3;              // compute warps have read S^T and dP^T out of tensor memory
-  // Fine-grained hand-offs, so that the four warps sharing a scheduler can drift apart and overlap their TMEM / MUFU /
-  // store phases instead of meeting at one CTA-wide barrier per step:
-  uint64_t* pds_cq = s_full + 4;    // [4] query-column quarter cq: P^T cols / dS^T cols of all 128 keys written
-                                    //     (the K-chunks 2cq, 2cq+1 of the dV and dK GEMMs)
-  uint64_t* pds_q = s_full + 8;     // [4] key-row quarter q: dS^T rows written for all queries (K-chunks 2q, 2q+1 of dQ)
-  uint64_t* free_v = s_full + 12;   // [4] dV K-chunks of cq complete: P^T columns of cq may be overwritten
-  uint64_t* free_k = s_full + 16;   // [4] dK K-chunks of cq complete   } together: the dS^T block of warp (q, cq)
-  uint64_t* free_q = s_full + 20;   // [4] dQ K-chunks of q complete    } may be overwritten
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 24);
+  uint64_t* pds_ready = s_full + 4;  // P^T (tensor memory) and dS^T (smem) of a step are written (16 warps)
+  uint64_t* mma_done = s_full + 5;   // the dV, dK and dQ GEMMs of a step are complete (3 commits): P^T columns and the
+                                     // dS^T buffer may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
 
   if ((smem_u32(smem) & 1023u) != 0) return;
 
@@ -222,15 +224,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
     mbar_init(s_full, 1);
     mbar_init(dq_full, 1);
-    mbar_init(dq_empty, AB_CWARPS);
+    mbar_init(dq_empty, 4);  // the four drain warps
     mbar_init(sdp_free, AB_CWARPS);
-    for (int g = 0; g < 4; ++g) {
-      mbar_init(&pds_cq[g], 4);
-      mbar_init(&pds_q[g], 4);
-      mbar_init(&free_v[g], 1);
-      mbar_init(&free_k[g], 1);
-      mbar_init(&free_q[g], 1);
-    }
+    mbar_init(pds_ready, AB_CWARPS);
+    mbar_init(mma_done, 3);
     fence_barrier_init();
   }
   if (warp == AB_W_MMA_S) {
@@ -241,11 +238,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // 768 threads leave 80 registers per thread; the compute warpgroups need 96 and take them from the auxiliary ones
+  // (setmaxnreg at the top of each role's branch)
   // TMEM columns: S^T 0..127 | dP^T 128..255 | dV 256..319 | dK 320..383 | dQ 384..447 | P^T (bf16 pairs) 448..511
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
                  tDQ = tmem_base + 384, tP = tmem_base + 448;
 
   if (warp == AB_W_TMA) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AB_REGS_AUX));
     // ------------------------------------------------------------ producer warp: lane 0 drives TMA (K,V once; Q_i,dO_i
     // ring), all 32 lanes stage the per-query vectors (lse*log2e, delta, seg_start) of the step next to its tiles.
     if (lane == 0) {
@@ -276,10 +276,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       if (++st == AB_STAGES) st = 0;
     }
   } else if (warp == AB_W_MMA_S) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AB_REGS_AUX));
     // ------------------------------------------------------------ MMA issuer 1: S^T = K Q^T, dP^T = V dO^T, dQ = dS K.
     // S^T / dP^T of step it+1 only wait for step it's tiles to be READ out of tensor memory (sdp_free, early in the
     // step); dQ of step it waits for its dS^T (pds_ready, late in the step) and for the previous dQ to have left tensor
-    // memory (dq_empty) — the two jobs never compete for this thread.  dQ: A = the dS^T buffer read MN-major (M =
+    // memory (dq_empty, signalled by the drain warps) — the two jobs never compete for this thread.  dQ: A = the dS^T buffer read MN-major (M =
     // queries, 64 per block, blocks AB_TILE apart), B = K MN-major.
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // K-major x K-major, N = 128 queries
@@ -312,22 +313,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         }
         if (it > 0) {  // dQ of step it-1
           const int pit = it - 1;
+          mbar_wait(pds_ready, pit & 1);
           if (pit > 0) mbar_wait(dq_empty, (pit - 1) & 1);
+          tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < AB_T / 16; ++k) {
-            if ((k & 1) == 0) {  // K-chunk k = key rows [16k, 16k+16): written by the warps of lane quarter k/2
-              mbar_wait(&pds_q[k >> 1], pit & 1);
-              tc_fence_after();
-            }
+          for (int k = 0; k < AB_T / 16; ++k)
             umma_ss(tDQ, ds_desc_mn + k * (2048 >> 4), k_desc_mn + k * (2048 >> 4), idesc_nn, k > 0 ? 1u : 0u);
-            if (k & 1) umma_commit(&free_q[k >> 1]);
-          }
           umma_commit(dq_full);
+          umma_commit(mma_done);
           AB_TR(64 + (it - 6) * 4 + 3);
         }
       }
     }
   } else if (warp == AB_W_MMA_DV) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AB_REGS_AUX));
     // ------------------------------------------------------------ MMA issuer 2: dV += P^T dO (A = P^T from tensor memory)
     if (lane == 0) {
       constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);   // A K-major (TMEM), B MN-major, N = 64
@@ -335,22 +334,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       int st = 0;
       for (int it = 0; it < n_it; ++it) {
         const uint64_t do_desc = do_desc0 + st * (AB_TILE >> 4);
+        mbar_wait(pds_ready, it & 1);
+        AB_TR(96 + (it - 6) * 4 + 0);
+        tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k) {
-          if ((k & 1) == 0) {  // K-chunk k = queries [16k, 16k+16): P^T columns written by the warps of column quarter k/2
-            mbar_wait(&pds_cq[k >> 1], it & 1);
-            if (k == 0) AB_TR(96 + (it - 6) * 4 + 0);
-            tc_fence_after();
-          }
+        for (int k = 0; k < AB_T / 16; ++k)
           umma_ts(tDV, tP + k * 8, do_desc + k * (2048 >> 4), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
-          if (k & 1) umma_commit(&free_v[k >> 1]);
-        }
+        umma_commit(mma_done);
         umma_commit(&qdo_empty[st]);
         AB_TR(96 + (it - 6) * 4 + 1);
         if (++st == AB_STAGES) st = 0;
       }
     }
   } else if (warp == AB_W_MMA_DK) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AB_REGS_AUX));
     // ------------------------------------------------------------ MMA issuer 3: dK += dS^T Q
     if (lane == 0) {
       constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);   // A K-major, B MN-major, N = 64
@@ -359,57 +356,62 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       int st = 0;
       for (int it = 0; it < n_it; ++it) {
         const uint64_t q_desc = q_desc0 + st * (AB_TILE >> 4);
+        mbar_wait(pds_ready, it & 1);
+        AB_TR(128 + (it - 6) * 4 + 0);
+        tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < AB_T / 16; ++k) {
-          if ((k & 1) == 0) {
-            mbar_wait(&pds_cq[k >> 1], it & 1);
-            if (k == 0) AB_TR(128 + (it - 6) * 4 + 0);
-            tc_fence_after();
-          }
+        for (int k = 0; k < AB_T / 16; ++k)
           umma_ss(tDK, ds_desc_k + ((k >> 2) * AB_TILE + (k & 3) * 32) / 16, q_desc + k * (2048 >> 4), idesc_kn,
                   (it > 0 || k > 0) ? 1u : 0u);
-          if (k & 1) umma_commit(&free_k[k >> 1]);
-        }
+        umma_commit(mma_done);
         umma_commit(&qdo_empty[st]);
         AB_TR(128 + (it - 6) * 4 + 1);
         if (++st == AB_STAGES) st = 0;
       }
     }
+  } else if (warp >= AB_W_DRAIN) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AB_REGS_AUX));
+    // ------------------------------------------------------------ dQ drain warps (one per TMEM lane quarter), off the
+    // compute warps' serial chain: dQ_i of a step leaves tensor memory (-> dq_empty: the next dQ GEMM may start), is
+    // staged as two 128B-swizzled [32 rows x 32] fp32 blocks and added into dq_acc by two TMA bulk reduce-adds.
+    // Lane r = QUERY row r.  Rows beyond T hold exact zeros (P is masked to 0 there), so adding them is harmless.
+    const int quarter = warp & 3;
+    uint8_t* blk = sDQ + quarter * (AB_DQ_STAGE / 4);
+    for (int it = 0; it < n_it; ++it) {
+      mbar_wait(dq_full, it & 1);
+      tc_fence_after();
+      if (lane == 0) bulk_wait_group_read<0>();  // the previous step's reduce-adds have finished reading the blocks
+      __syncwarp();
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {  // 16 head-dim columns at a time (these warps run on 48 registers)
+        uint32_t t[16];
+        tmem_ld16(tDQ + (static_cast<uint32_t>(quarter * 32) << 16) + qq * 16, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          *reinterpret_cast<uint4*>(blk + (qq >> 1) * 4096 + lane * 128 + ((((qq & 1) * 4 + c) ^ (lane & 7)) << 4)) =
+              make_uint4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(dq_empty);
+        const int row0 = static_cast<int>(seq0 + (j + it) * AB_T + quarter * 32);
+        tma_reduce_add_2d(&tmDQ, blk, h * AB_HD, row0);
+        tma_reduce_add_2d(&tmDQ, blk + 4096, h * AB_HD + 32, row0);
+        bulk_commit_group();
+      }
+    }
+    if (lane == 0) bulk_wait_group<0>();  // the reduce-adds have landed
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AB_REGS_COMPUTE));
     // ------------------------------------------------------------ compute warps (16): warp = (lane quarter, column quarter)
     const int quarter = warp & 3;
     const int cq = warp >> 2;                // query columns [32*cq, +32) of S^T / dP^T; hd cols [16*cq, +16) of dQ/dK/dV
     const int r = quarter * 32 + lane;       // key row within the tile (S^T lane) / query row within the tile (dQ lane)
     const int kj = j * AB_T + r;             // key position
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-
-    // dQ of query tile i_tile leaves through TMA reduce-adds: lane r now means QUERY row r, 16 head-dim columns per
-    // thread.  Each warp stages its own [32 rows x 16] fp32 block (64-byte swizzle) and issues one bulk reduce-add into
-    // dq_acc — no strided red.global traffic, no cross-warp synchronisation, and tensor memory is released (dq_empty)
-    // as soon as the values are in registers.  Rows beyond T hold exact zeros (P is masked to 0 there).
-    uint8_t* dq_blk = sDQ + warp * (AB_DQ_STAGE / AB_CWARPS);
-    auto dq_flush = [&](int i_tile, bool release) {
-      uint32_t t[16];
-      tmem_ld16(tDQ + lane_off + cq * 16, t);
-      tmem_ld_wait();
-      if (release) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dq_empty);
-      }
-      if (lane == 0) bulk_wait_group_read<0>();  // this warp's previous reduce-add has finished reading the block
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(dq_blk + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
-            make_uint4(t[4 * c], t[4 * c + 1], t[4 * c + 2], t[4 * c + 3]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_reduce_add_2d(&tmDQ, dq_blk, h * AB_HD + cq * 16, static_cast<int>(seq0 + i_tile * AB_T + quarter * 32));
-        bulk_commit_group();
-      }
-    };
 
     int st = 0;
     for (int it = 0; it < n_it; ++it) {
@@ -469,9 +471,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       AB_TRC(4);
       // the previous step's dV MMAs must be done with this warp's P^T columns, its dK / dQ MMAs with its dS^T block
       if (it > 0) {
-        mbar_wait(&free_v[cq], (it - 1) & 1);
-        mbar_wait(&free_k[cq], (it - 1) & 1);
-        mbar_wait(&free_q[quarter], (it - 1) & 1);
+        mbar_wait(mma_done, (it - 1) & 1);
         tc_fence_after();
       }
       AB_TRC(5);
@@ -481,32 +481,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {  // hand-off out
-        mbar_arrive(&pds_cq[cq]);
-        mbar_arrive(&pds_q[quarter]);
-      }
+      if (lane == 0) mbar_arrive(pds_ready);  // one hand-off out
       AB_TRC(6);
       if (tr_on && it >= 6 && it < 10 && lane == 0) g_dbg_counters[192 + (it - 6) * 16 + warp] = clock64();
 
-      // dQ of the previous step: out of tensor memory first (unblocks this step's dQ MMAs), then off to dq_acc
-      if (it > 0) {
-        mbar_wait(dq_full, (it - 1) & 1);
-        tc_fence_after();
-        dq_flush(i - 1, true);
-      }
       AB_TRC(7);
       if (++st == AB_STAGES) st = 0;
     }
 
-    // ---- tail: dQ of the last step, then dV / dK of this key tile (16 head-dim columns per thread)
-    mbar_wait(dq_full, (n_it - 1) & 1);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {  // every K-chunk of the last dV / dK GEMMs
-      mbar_wait(&free_v[g], (n_it - 1) & 1);
-      mbar_wait(&free_k[g], (n_it - 1) & 1);
-    }
+    // ---- tail: dV / dK of this key tile (16 head-dim columns per thread)
+    mbar_wait(mma_done, (n_it - 1) & 1);
     tc_fence_after();
-    dq_flush(j + n_it - 1, false);
     const bool k_ok = kj < T;
     {
       uint32_t t[16];
@@ -560,7 +545,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   }
 
-  if (warp < AB_CWARPS && lane == 0) bulk_wait_group<0>();  // dQ reduce-adds have landed
   tc_fence_before();
   __syncthreads();
   if (warp == AB_W_MMA_S) {
@@ -611,8 +595,8 @@ extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, 
   if (rc != PLM_OK) return rc;
   rc = make_tmap_bf16_2d(&tmDO, dout, rows, d, d, AB_T, 64);
   if (rc != PLM_OK) return rc;
-  CUtensorMap tmDQ;  // dq_acc fp32 [rows, d]: boxes of 32 rows x 16 columns (one compute warp's share) for the reduce-adds
-  rc = make_tmap_f32_2d(&tmDQ, dq_acc, rows, d, d, 32, 16);
+  CUtensorMap tmDQ;  // dq_acc fp32 [rows, d]: boxes of 32 rows x 32 columns (half of one drain warp's share) for the reduce-adds
+  rc = make_tmap_f32_2d(&tmDQ, dq_acc, rows, d, d, 32, 32);
   if (rc != PLM_OK) return rc;
 
   cudaError_t e = cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * d * sizeof(float), stream);
