@@ -518,6 +518,37 @@ def case_gemm_feed_probe():
   return results
 
 
+def case_gemm_n1024_probe():
+  """N = 1024 outputs make 512 tiles of 128x256 = 3.46 waves on 148 SMs: does BN = 128 (6.9 waves) do better?"""
+  import torch
+  from plainlm_b200 import ops, _lib
+
+  dev = 'cuda'
+  M, d, F = 16384, 1024, 2816
+  bf = torch.bfloat16
+  res = torch.randn(M, d, device=dev)
+  outf = torch.empty(M, d, device=dev)
+  outb = torch.empty(M, d, device=dev, dtype=bf)
+  shapes = []
+  for K, bk, name in ((1024, True, 'out fwd+resid'), (2816, True, 'fc2 fwd+resid'), (1024, False, 'out dgrad'),
+                      (3072, False, 'qkv dgrad'), (5632, False, 'fc1 dgrad')):
+    a = torch.randn(M, K, device=dev).to(bf)
+    b = (torch.randn(d, K, device=dev) if bk else torch.randn(K, d, device=dev)).to(bf)
+    if 'resid' in name:
+      fn = (lambda a=a, b=b: ops.gemm(a, b, outf, epilogue=_lib.EPI_RESID_F32, residual=res))
+    else:
+      fn = (lambda a=a, b=b: ops.gemm(a, b, outb, a_kmajor=True, b_kmajor=False))
+    shapes.append((name, fn, 2.0 * M * d * K))
+  results = []
+  for bn in ('256', '128'):
+    os.environ['PLM_GEMM_BN'] = bn
+    for n, fn, fl in shapes:
+      ms = _time(fn, 10)
+      results.append({'case': f'{n} bn{bn}', 'ms': round(ms, 4), 'tflops': round(fl / ms / 1e9, 0)})
+  os.environ.pop('PLM_GEMM_BN')
+  return results
+
+
 def case_bw_perf():
   """Achieved GB/s of the bandwidth kernels at the 420M shapes (algorithmic bytes / CUDA-event time)."""
   import torch
@@ -696,6 +727,7 @@ CASES['attn_perf'] = case_attn_perf
 CASES['bw_perf'] = case_bw_perf
 CASES['gemm_epi_perf'] = case_gemm_epi_perf
 CASES['gemm_feed_probe'] = case_gemm_feed_probe
+CASES['gemm_n1024_probe'] = case_gemm_n1024_probe
 CASES['attn_bwd_trace'] = case_attn_bwd_trace
 CASES['gemm_sustained'] = case_gemm_sustained
 
