@@ -303,8 +303,16 @@ def run_ours(args):
     else:
       achieved = rec['work'] / (rec['ms'] / 1e3) / 1e9
       peak, unit, bound = peaks['hbm_gbs'], 'GB/s', 'hbm'
+    traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu pass (profiles/traffic.json)
+    try:
+      with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'traffic.json')) as f:
+        tj = json.load(f)
+      if args.config == '420m' and tj.get(name, {}).get('dram_bytes_per_call'):
+        traffic = round(tj[name]['dram_bytes_per_call'])
+    except (OSError, ValueError):
+      pass
     roofline = {'bound': bound, 'kernel': name, 'achieved': round(achieved, 1), 'peak': peak, 'unit': unit,
-                'frac': round(achieved / peak, 4), 'traffic': None, 'peak_source': peaks['source'] + ' (sustained)',
+                'frac': round(achieved / peak, 4), 'traffic': traffic, 'peak_source': peaks['source'] + ' (sustained)',
                 'share_of_step': round(rec['ms'] / total_ms, 3), 'avg_launch_ms': round(rec['ms'] / rec['calls'], 4),
                 'by_kernel_ms': {k: round(v['ms'], 2) for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1]['ms'])},
                 'by_kernel_frac': {k: round((v['work'] / (v['ms'] / 1e3) / (1e12 if v['kind'] == 'tensor' else 1e9)) /

@@ -31,8 +31,13 @@ elif which == 'gemm':
   du = torch.randn(M, 2 * F, device=dev).to(bf)
   dw = torch.zeros(2 * F, d, device=dev)
   dx = torch.empty(M, d, device=dev, dtype=bf)
+  g = torch.empty(M, F, device=dev, dtype=bf)
+  res = torch.randn(M, d, device=dev)
+  xo = torch.empty(M, d, device=dev)
+  w2 = torch.randn(d, F, device=dev).to(bf)
   for _ in range(2):
-    ops.gemm(x, w1, u)                                                                      # fwd  (K,K)
+    ops.gemm(x, w1, u, epilogue=_lib.EPI_BF16_SWIGLU, out2=g)                               # fc1 fwd + GLU gate
+    ops.gemm(g, w2, xo, epilogue=_lib.EPI_RESID_F32, residual=res)                          # fc2 fwd + residual
     ops.gemm(du, w1, dx, a_kmajor=True, b_kmajor=False)                                     # dgrad (K,MN)
     ops.gemm(du, x, dw, a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ATOMIC_F32, splits=0)  # wgrad (MN,MN)
 elif which == 'norm':
