@@ -139,6 +139,14 @@ int plm_swiglu_fwd(const void* u, void* h, int64_t rows, int32_t F, plm_stream_t
 /* du = [dh * z * silu'(a) | dh * silu(a)] (bf16 [rows, 2F]). */
 int plm_swiglu_bwd(const void* dh, const void* u, void* du, int64_t rows, int32_t F, plm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------ plain MLPs
+ * models/components.py:31-40 (MLP: h = silu(u)) and :59-70 (MLPReluSquared: h = relu(u)^2); u, h, dh, du bf16 [n].
+ * bwd: du = dh * act'(u). */
+#define PLM_ACT_SILU 0
+#define PLM_ACT_RELU2 1
+int plm_act_fwd(const void* u, void* h, int64_t n, int32_t kind, plm_stream_t stream);
+int plm_act_bwd(const void* dh, const void* u, void* du, int64_t n, int32_t kind, plm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ embedding
  * models/transformer.py:110 nn.Embedding: x[r, :] = W[ids[r], :] (fp32 residual stream); ids are int64. */
 int plm_embed_fwd(const int64_t* ids, const float* W, float* x, int64_t rows, int32_t d, int64_t vocab,
@@ -175,6 +183,23 @@ int plm_adamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, i
 int plm_signsgd_step(float* p, const float* g, float* m, void* p_bf16, int64_t n, float lr, float momentum,
                      float dampening, float weight_decay, int32_t first_step, const float* gnorm_sq, float max_norm,
                      plm_stream_t stream);
+
+/* torch.optim.NAdam(decoupled_weight_decay=True) as built at optim/init_optim.py:23-32 ("nadamw"), flat:
+ *   p *= 1 - lr*wd;  m += (1-beta1)(g - m);  v = beta2 v + (1-beta2) g^2;  denom = sqrt(v / bc2) + eps;
+ *   p += c_grad * g / denom;  p += c_mom * m / denom
+ * with the host-side scalars of step t (torch/optim/nadam.py _single_tensor_nadam): bc2 = 1 - beta2^t,
+ * mu_t = beta1 (1 - 0.5 * 0.96^(t * momentum_decay)), c_grad = -lr (1 - mu_t) / (1 - prod_{s<=t} mu_s),
+ * c_mom = -lr mu_{t+1} / (1 - prod_{s<=t+1} mu_s).  Gradient clipping / bf16 shadow as in plm_adamw_step. */
+int plm_nadamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, float bc2, float c_grad, float c_mom,
+                    const float* gnorm_sq, float max_norm, plm_stream_t stream);
+
+/* torch.optim.SGD(momentum, dampening, weight_decay) as built at optim/init_optim.py:34-41, flat:
+ *   g += wd * p;  buf = first_step ? g : momentum * buf + (1 - dampening) * g;  p -= lr * buf
+ * (momentum == 0: p -= lr * g, buf untouched).  Gradient clipping / bf16 shadow as in plm_adamw_step. */
+int plm_sgd_step(float* p, const float* g, float* buf, void* p_bf16, int64_t n, float lr, float momentum,
+                 float dampening, float weight_decay, int32_t first_step, const float* gnorm_sq, float max_norm,
+                 plm_stream_t stream);
 
 /* fp32 -> bf16 shadow copy of a flat buffer (initial weight cast; autocast's per-step cast in the reference). */
 int plm_cast_f32_bf16(const float* src, void* dst, int64_t n, float scale, plm_stream_t stream);

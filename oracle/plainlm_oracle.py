@@ -49,7 +49,7 @@ def param_names(n_layers):
   return names
 
 
-def init_params(vocab, dim, n_layers, n_heads, seed=0, expand=8 / 3):
+def init_params(vocab, dim, n_layers, n_heads, seed=0, expand=8 / 3, mlp_class='glu'):
   """Random parameters with the reference's init statistics (transformer.py:116-129): N(0, 0.02), residual output
   projections N(0, 0.02/sqrt(2L)), norm weights 1.  (Not the reference's RNG stream: parity tests share a state_dict.)"""
   g = torch.Generator().manual_seed(seed)
@@ -60,7 +60,8 @@ def init_params(vocab, dim, n_layers, n_heads, seed=0, expand=8 / 3):
     p[f'layers.{i}.attn.w_qkv.weight'] = torch.randn(3 * dim, dim, generator=g) * 0.02
     p[f'layers.{i}.attn.w_out.weight'] = torch.randn(dim, dim, generator=g) * std_out
     p[f'layers.{i}.attn_norm.weight'] = torch.ones(dim)
-    p[f'layers.{i}.mlp.fc1.weight'] = torch.randn(2 * Fh, dim, generator=g) * 0.02
+    fc1_rows = 2 * Fh if mlp_class == 'glu' else Fh  # components.py:50 vs :35,66
+    p[f'layers.{i}.mlp.fc1.weight'] = torch.randn(fc1_rows, dim, generator=g) * 0.02
     p[f'layers.{i}.mlp.fc2.weight'] = torch.randn(dim, Fh, generator=g) * std_out
     p[f'layers.{i}.mlp_norm.weight'] = torch.ones(dim)
   p['out_norm.weight'] = torch.ones(dim)
@@ -165,7 +166,14 @@ def glu(x, w1, w2, precision='fp32'):
   return _linear(F.silu(a) * z, w2, precision)
 
 
-def forward(params, ids, n_heads, mask=None, precision='fp32'):
+def mlp_plain(x, w1, w2, mlp_class, precision='fp32'):
+  """models/components.py:38-40 (MLP: fc2(silu(fc1 x))) and :68-70 (MLPReluSquared: fc2(relu(fc1 x)^2))."""
+  u = _linear(x, w1, precision)
+  h = F.silu(u) if mlp_class == 'mlp' else F.relu(u).pow(2)
+  return _linear(h, w2, precision)
+
+
+def forward(params, ids, n_heads, mask=None, precision='fp32', mlp_class='glu'):
   """models/transformer.py:108-114 (+ Block.forward :79-83). ids int64 [B,T]; mask bool [B,T,T] or None.
   Returns logits [B,T,V] (bf16 under precision='bf16', as autocast produces)."""
   n_layers = sum(1 for k in params if k.endswith('attn_norm.weight'))
@@ -179,7 +187,10 @@ def forward(params, ids, n_heads, mask=None, precision='fp32'):
     x = x + attention(h, params[pre + 'attn.w_qkv.weight'], params[pre + 'attn.w_out.weight'], table, n_heads, m,
                       precision)
     h = rmsnorm(x, params[pre + 'mlp_norm.weight'])
-    x = x + glu(h, params[pre + 'mlp.fc1.weight'], params[pre + 'mlp.fc2.weight'], precision)
+    if mlp_class == 'glu':
+      x = x + glu(h, params[pre + 'mlp.fc1.weight'], params[pre + 'mlp.fc2.weight'], precision)
+    else:
+      x = x + mlp_plain(h, params[pre + 'mlp.fc1.weight'], params[pre + 'mlp.fc2.weight'], mlp_class, precision)
   return _linear(rmsnorm(x, params['out_norm.weight']), params['lm_head.weight'], precision)
 
 
@@ -221,6 +232,35 @@ def signsgd_step(p, g, m, first, lr, momentum, dampening, weight_decay):
     m.copy_(g)
   m.mul_(momentum).add_(g, alpha=1.0 - dampening)
   p.add_(torch.sign(m), alpha=-lr)
+
+
+def nadamw_step(p, g, m, v, state, lr, beta1, beta2, eps, weight_decay, momentum_decay=4e-3):
+  """torch.optim.NAdam(decoupled_weight_decay=True) single-tensor update (torch/optim/nadam.py _single_tensor_nadam),
+  what optim/init_optim.py:23-32 builds for cfg.optim == 'nadamw'.  state: {'step': int, 'mu_product': float}."""
+  state['step'] = step = state.get('step', 0) + 1
+  bc2 = 1 - beta2**step
+  p.mul_(1 - lr * weight_decay)
+  mu = beta1 * (1.0 - 0.5 * (0.96 ** (step * momentum_decay)))
+  mu_next = beta1 * (1.0 - 0.5 * (0.96 ** ((step + 1) * momentum_decay)))
+  state['mu_product'] = prod = state.get('mu_product', 1.0) * mu
+  m.lerp_(g, 1 - beta1)
+  v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+  denom = v.div(bc2).sqrt().add_(eps)
+  p.addcdiv_(g, denom, value=-lr * (1.0 - mu) / (1.0 - prod))
+  p.addcdiv_(m, denom, value=-lr * mu_next / (1.0 - prod * mu_next))
+
+
+def sgd_step(p, g, buf, first, lr, momentum, dampening, weight_decay):
+  """torch.optim.SGD single-tensor update (torch/optim/sgd.py), as built at optim/init_optim.py:34-41: coupled L2
+  weight decay, momentum buffer initialised to a clone of the first (decayed) gradient, no Nesterov."""
+  g = g.add(p, alpha=weight_decay) if weight_decay != 0 else g
+  if momentum != 0:
+    if first:
+      buf.copy_(g)
+    else:
+      buf.mul_(momentum).add_(g, alpha=1 - dampening)
+    g = buf
+  p.add_(g, alpha=-lr)
 
 
 def warmup_cosine_lr(t, lr_start, lr_max, lr_end, warmup_steps, T):

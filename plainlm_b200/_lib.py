@@ -14,6 +14,7 @@ CSRC_DIR = os.path.join(_HERE, 'csrc')
 PLM_OK = 0
 EPI_BF16, EPI_BF16_ROPE, EPI_F32, EPI_RESID_F32, EPI_ATOMIC_F32, EPI_BF16_SWIGLU = range(6)
 SUMSQ_WORKSPACE = 1024
+ACT_SILU, ACT_RELU2 = 0, 1
 
 c_void_p, c_int32, c_int64, c_float = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 
@@ -46,12 +47,16 @@ SIGNATURES = {
   'plm_colsum_accum_batched': (c_int32, [_P, _P, _I32, _I32, _I32, _P]),
   'plm_swiglu_fwd': (c_int32, [_P, _P, _I64, _I32, _P]),
   'plm_swiglu_bwd': (c_int32, [_P, _P, _P, _I64, _I32, _P]),
+  'plm_act_fwd': (c_int32, [_P, _P, _I64, _I32, _P]),
+  'plm_act_bwd': (c_int32, [_P, _P, _P, _I64, _I32, _P]),
   'plm_embed_fwd': (c_int32, [_P, _P, _P, _I64, _I32, _I64, _P]),
   'plm_embed_bwd': (c_int32, [_P, _P, _P, _I64, _I32, _I64, _P]),
   'plm_ce_fwd_bwd': (c_int32, [_P, _P, _P, _P, _P, _I64, _I32, _I64, _F, _I32, _P]),
   'plm_sumsq': (c_int32, [_P, _I64, _P, _P, _I32, _P]),
   'plm_adamw_step': (c_int32, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _F, _P, _F, _P]),
   'plm_signsgd_step': (c_int32, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _P, _F, _P]),
+  'plm_nadamw_step': (c_int32, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _F, _F, _P, _F, _P]),
+  'plm_sgd_step': (c_int32, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _P, _F, _P]),
   'plm_cast_f32_bf16': (c_int32, [_P, _P, _I64, _F, _P]),
   'plm_cast_bf16_f32': (c_int32, [_P, _P, _I64, _F, _P]),
   'plm_seg_start_from_lengths': (c_int32, [_P, _P, _P, _I32, _I32, _P]),

@@ -58,6 +58,51 @@ swiglu_bwd_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ u, uin
   du[r * (2 * F8) + F8 + c] = make_uint4(dz[0], dz[1], dz[2], dz[3]);
 }
 
+// ------------------------------------------------------------------------------------------- plain MLP activations
+// models/components.py:31-40 (MLP: silu) and :59-70 (MLPReluSquared: relu(u)^2).  KIND 0 = silu, 1 = relu squared.
+template <int KIND>
+__device__ __forceinline__ float act_f(float a) {
+  if (KIND == 0) return a * sigmoidf_fast(a);
+  const float r = fmaxf(a, 0.f);
+  return r * r;
+}
+template <int KIND>
+__device__ __forceinline__ float act_df(float a) {
+  if (KIND == 0) {
+    const float s = sigmoidf_fast(a);
+    return s + a * s * (1.f - s);
+  }
+  return 2.f * fmaxf(a, 0.f);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const uint4* __restrict__ u, uint4* __restrict__ h, int64_t n8) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n8) return;
+  const uint4 a = __ldcs(u + idx);
+  const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = pack_bf16x2(act_f<KIND>(bf16_lo(av[i])), act_f<KIND>(bf16_hi(av[i])));
+  h[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const uint4* __restrict__ dh, const uint4* __restrict__ u, uint4* __restrict__ du, int64_t n8) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n8) return;
+  const uint4 a = __ldcs(u + idx);
+  const uint4 g = __ldcs(dh + idx);
+  const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+  const uint32_t gv[4] = {g.x, g.y, g.z, g.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    o[i] = pack_bf16x2(bf16_lo(gv[i]) * act_df<KIND>(bf16_lo(av[i])), bf16_hi(gv[i]) * act_df<KIND>(bf16_hi(av[i])));
+  du[idx] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // ------------------------------------------------------------------------------------------- embedding
 __global__ void __launch_bounds__(256)
 embed_fwd_kernel(const int64_t* __restrict__ ids, const float4* __restrict__ W, float4* __restrict__ x, int64_t rows,
@@ -209,6 +254,43 @@ int plm_swiglu_bwd(const void* dh, const void* u, void* du, int64_t rows, int32_
   swiglu_bwd_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
       static_cast<const uint4*>(dh), static_cast<const uint4*>(u), static_cast<uint4*>(du), rows, F / 8);
   return check_launch("swiglu_bwd");
+}
+
+int plm_act_fwd(const void* u, void* h, int64_t n, int32_t kind, plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(u);
+  PLM_REQUIRE(u && h && n >= 0, "act_fwd: bad argument");
+  PLM_REQUIRE(kind == PLM_ACT_SILU || kind == PLM_ACT_RELU2, "act_fwd: unknown activation %d", kind);
+  PLM_REQUIRE(n % 8 == 0 && aligned16(u) && aligned16(h), "act_fwd: n %% 8 and 16-byte alignment required");
+  if (n == 0) return PLM_OK;
+  const int64_t n8 = n / 8;
+  const unsigned grid = static_cast<unsigned>((n8 + 255) / 256);
+  if (kind == PLM_ACT_SILU)
+    act_fwd_kernel<0><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(u), static_cast<uint4*>(h), n8);
+  else
+    act_fwd_kernel<1><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(u), static_cast<uint4*>(h), n8);
+  return check_launch("act_fwd");
+}
+
+int plm_act_bwd(const void* dh, const void* u, void* du, int64_t n, int32_t kind, plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(u);
+  PLM_REQUIRE(dh && u && du && n >= 0, "act_bwd: bad argument");
+  PLM_REQUIRE(kind == PLM_ACT_SILU || kind == PLM_ACT_RELU2, "act_bwd: unknown activation %d", kind);
+  PLM_REQUIRE(n % 8 == 0 && aligned16(u) && aligned16(dh) && aligned16(du),
+              "act_bwd: n %% 8 and 16-byte alignment required");
+  if (n == 0) return PLM_OK;
+  const int64_t n8 = n / 8;
+  const unsigned grid = static_cast<unsigned>((n8 + 255) / 256);
+  if (kind == PLM_ACT_SILU)
+    act_bwd_kernel<0><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(dh), static_cast<const uint4*>(u),
+                                                static_cast<uint4*>(du), n8);
+  else
+    act_bwd_kernel<1><<<grid, 256, 0, stream>>>(static_cast<const uint4*>(dh), static_cast<const uint4*>(u),
+                                                static_cast<uint4*>(du), n8);
+  return check_launch("act_bwd");
 }
 
 int plm_embed_fwd(const int64_t* ids, const float* W, float* x, int64_t rows, int32_t d, int64_t vocab,

@@ -273,6 +273,75 @@ signsgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __rest
   }
 }
 
+// ---- NAdam with decoupled weight decay (torch.optim.NAdam(decoupled_weight_decay=True), optim/init_optim.py:23-32)
+// and SGD with momentum (torch.optim.SGD, init_optim.py:34-41) share one flat kernel shape.
+struct NAdamArgs {
+  float decay, one_minus_b1, b2, one_minus_b2, eps, inv_bc2, c_grad, c_mom, max_norm;
+};
+struct NAdamOp {
+  NAdamArgs a;
+  __device__ __forceinline__ void operator()(float& p, float g, float& m, float& v) const {
+    p *= a.decay;
+    m = m + a.one_minus_b1 * (g - m);
+    v = a.b2 * v + a.one_minus_b2 * g * g;
+    const float denom = sqrtf(v * a.inv_bc2) + a.eps;
+    p += a.c_grad * g / denom;  // torch: two addcdiv_ calls, grad first
+    p += a.c_mom * m / denom;
+  }
+};
+struct SgdArgs {
+  float lr, momentum, one_minus_damp, wd, max_norm;
+  int first, use_momentum;
+};
+struct SgdOp {
+  SgdArgs a;
+  __device__ __forceinline__ void operator()(float& p, float g, float& buf, float&) const {
+    g = g + a.wd * p;  // coupled (L2) weight decay
+    if (a.use_momentum) {
+      buf = a.first ? g : a.momentum * buf + a.one_minus_damp * g;  // torch: buffer starts as a clone of the gradient
+      g = buf;
+    }
+    p -= a.lr * g;
+  }
+};
+
+template <class Op, bool HAS_V>
+__global__ void __launch_bounds__(256)
+flat_opt_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                __nv_bfloat16* __restrict__ pb, int64_t n, Op op, float max_norm, const float* __restrict__ gnorm_sq) {
+  const float clip = clip_coef(gnorm_sq, max_norm);
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    const float4 gv = __ldcs(reinterpret_cast<const float4*>(g) + i);
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = HAS_V ? reinterpret_cast<float4*>(v)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    op(pv.x, gv.x * clip, mv.x, vv.x);
+    op(pv.y, gv.y * clip, mv.y, vv.y);
+    op(pv.z, gv.z * clip, mv.z, vv.z);
+    op(pv.w, gv.w * clip, mv.w, vv.w);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    if (HAS_V) reinterpret_cast<float4*>(v)[i] = vv;
+    if (pb) {
+      uint2 o;
+      o.x = pack_bf16x2(pv.x, pv.y);
+      o.y = pack_bf16x2(pv.z, pv.w);
+      reinterpret_cast<uint2*>(pb)[i] = o;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    float pv = p[i], mv = m[i], vv = HAS_V ? v[i] : 0.f;
+    op(pv, g[i] * clip, mv, vv);
+    p[i] = pv;
+    m[i] = mv;
+    if (HAS_V) v[i] = vv;
+    if (pb) pb[i] = __float2bfloat16_rn(pv);
+  }
+}
+
 static unsigned flat_grid(int64_t n4) {
   int64_t blocks = (n4 + 255) / 256;
   const int64_t cap = static_cast<int64_t>(sm_count()) * 8;
@@ -363,6 +432,54 @@ int plm_signsgd_step(float* p, const float* g, float* m, void* p_bf16, int64_t n
                                                          first_step ? 1 : 0,
                                                          gnorm_sq, max_norm);
   return check_launch("signsgd");
+}
+
+int plm_nadamw_step(float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, float bc2, float c_grad, float c_mom,
+                    const float* gnorm_sq, float max_norm, plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(p);
+  PLM_REQUIRE(p && g && m && v && n >= 0, "nadamw: bad argument");
+  PLM_REQUIRE(aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v), "nadamw: misaligned pointer");
+  PLM_REQUIRE(!p_bf16 || (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0, "nadamw: misaligned bf16 shadow");
+  PLM_REQUIRE(bc2 > 0.f, "nadamw: bias correction must be positive (step >= 1)");
+  if (n == 0) return PLM_OK;
+  NAdamOp op;
+  op.a.decay = static_cast<float>(1.0 - static_cast<double>(lr) * weight_decay);
+  op.a.one_minus_b1 = static_cast<float>(1.0 - static_cast<double>(beta1));
+  op.a.b2 = beta2;
+  op.a.one_minus_b2 = static_cast<float>(1.0 - static_cast<double>(beta2));
+  op.a.eps = eps;
+  op.a.inv_bc2 = 1.0f / bc2;
+  op.a.c_grad = c_grad;
+  op.a.c_mom = c_mom;
+  flat_opt_kernel<NAdamOp, true><<<flat_grid(n >> 2), 256, 0, stream>>>(p, g, m, v, static_cast<__nv_bfloat16*>(p_bf16),
+                                                                         n, op, max_norm, gnorm_sq);
+  return check_launch("nadamw");
+}
+
+int plm_sgd_step(float* p, const float* g, float* buf, void* p_bf16, int64_t n, float lr, float momentum,
+                 float dampening, float weight_decay, int32_t first_step, const float* gnorm_sq, float max_norm,
+                 plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(p);
+  PLM_REQUIRE(p && g && buf && n >= 0, "sgd: bad argument");
+  PLM_REQUIRE(aligned16(p) && aligned16(g) && aligned16(buf), "sgd: misaligned pointer");
+  PLM_REQUIRE(!p_bf16 || (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0, "sgd: misaligned bf16 shadow");
+  if (n == 0) return PLM_OK;
+  SgdOp op;
+  op.a.lr = lr;
+  op.a.momentum = momentum;
+  op.a.one_minus_damp = static_cast<float>(1.0 - static_cast<double>(dampening));
+  op.a.wd = weight_decay;
+  op.a.first = first_step ? 1 : 0;
+  op.a.use_momentum = momentum != 0.f ? 1 : 0;
+  flat_opt_kernel<SgdOp, false><<<flat_grid(n >> 2), 256, 0, stream>>>(p, g, buf, nullptr,
+                                                                        static_cast<__nv_bfloat16*>(p_bf16), n, op,
+                                                                        max_norm, gnorm_sq);
+  return check_launch("sgd");
 }
 
 }  // extern "C"

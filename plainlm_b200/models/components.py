@@ -7,6 +7,7 @@ Each `forward` here is the stand-alone entry used when a block is called outside
 import torch
 from torch import nn
 
+from .. import _lib
 from . import functional as PF
 
 
@@ -38,17 +39,29 @@ class GLU(nn.Module):
     return PF.linear(PF.swiglu(u), self.fc2.weight)
 
 
-class MLP(nn.Module):
-  """reference: models/components.py:31-40. Constructor kept for config compatibility; SURVEY.md §8(f) N4 ("next")."""
+class _PlainMLP(nn.Module):
+  """fc2(act(fc1 x)) with a single-branch activation (kernel: plm_act_fwd / plm_act_bwd)."""
+
+  act_kind = None  # _lib.ACT_*
 
   def __init__(self, dim: int, hidden_dim: int, multiple_of: int = 256):
     super().__init__()
-    raise NotImplementedError("mlp_class 'mlp' is outside the B200 hot path (use 'glu'); SURVEY.md §8(f) N4")
+    hidden_dim = multiple_of * ((hidden_dim + multiple_of - 1) // multiple_of)
+    self.hidden_dim = hidden_dim
+    self.fc1 = nn.Linear(dim, hidden_dim, bias=False)
+    self.fc2 = nn.Linear(hidden_dim, dim, bias=False)
+
+  def forward(self, x):
+    return PF.linear(PF.activation(PF.linear(x, self.fc1.weight), self.act_kind), self.fc2.weight)
 
 
-class MLPReluSquared(nn.Module):
-  """reference: models/components.py:59-70. See MLP."""
+class MLP(_PlainMLP):
+  """reference: models/components.py:31-40: fc2(silu(fc1 x))."""
 
-  def __init__(self, dim: int, hidden_dim: int, multiple_of: int = 256):
-    super().__init__()
-    raise NotImplementedError("mlp_class 'mlp_relu_sq' is outside the B200 hot path (use 'glu'); SURVEY.md §8(f) N4")
+  act_kind = _lib.ACT_SILU
+
+
+class MLPReluSquared(_PlainMLP):
+  """reference: models/components.py:59-70: fc2(relu(fc1 x)^2)."""
+
+  act_kind = _lib.ACT_RELU2

@@ -146,6 +146,29 @@ def swiglu(u):
   return _SwiGLU.apply(u)
 
 
+class _Activation(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, u, kind):
+    u2 = _flat2d(u).to(bf16).contiguous()
+    h = torch.empty_like(u2)
+    ops.act_fwd(u2, h, kind)
+    ctx.save_for_backward(u2)
+    ctx.shape, ctx.kind = u.shape, kind
+    return h.view(u.shape)
+
+  @staticmethod
+  def backward(ctx, dh):
+    (u2,) = ctx.saved_tensors
+    du = torch.empty_like(u2)
+    ops.act_bwd(_flat2d(dh).to(bf16).contiguous(), u2, du, ctx.kind)
+    return du.view(ctx.shape), None
+
+
+def activation(u, kind):
+  """silu(u) (MLP, components.py:40) or relu(u)^2 (MLPReluSquared, components.py:70); kind = _lib.ACT_*."""
+  return _Activation.apply(u, kind)
+
+
 # ------------------------------------------------------------------------------------------------- attention
 class _FlashAttention(torch.autograd.Function):
   @staticmethod

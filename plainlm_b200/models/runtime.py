@@ -120,7 +120,8 @@ class _Workspace:
     self.qkv = [e(M, 3 * d) for _ in range(L)]
     self.attn = [e(M, d) for _ in range(L)]
     self.lse = [e(B, H, T, dtype=f32) for _ in range(L)]
-    self.u = [e(M, 2 * F) for _ in range(L)]
+    U = rt.fc1_out  # 2F for the GLU (u = [a | z]), F for the single-branch MLPs
+    self.u = [e(M, U) for _ in range(L)]
     self.g = [e(M, F) for _ in range(L)]
     self.hf = e(M, d)
     self.rstd_f = e(M, dtype=f32)
@@ -133,7 +134,7 @@ class _Workspace:
     self.dx_b2 = [e(M, d), e(M, d)]  # ping-pong: the side-stream wgrad of one branch reads it while the next is written
     self.dh = e(M, d)
     self.dg = e(M, F)
-    self.du = e(M, 2 * F)
+    self.du = e(M, U)
     self.dattn = e(M, d)
     self.dqkv = e(M, 3 * d)
     self.delta = e(B, H, T, dtype=f32)
@@ -162,6 +163,9 @@ class TrainRuntime:
     gr = lambda n: p[n].grad  # noqa: E731
     self.names = p
     self.tied = model.lm_head.weight is model.embed_tokens.weight
+    mlp0 = model.layers[0].mlp if L else None
+    self.act_kind = getattr(mlp0, 'act_kind', None)  # None: GLU (fc1 -> [a | z]); else single-branch activation
+    self.fc1_out = (2 if self.act_kind is None else 1) * model.hidden_dim
     ns = self.flat.norm_start
     self.norm_grads = self.flat.grads[ns : ns + (2 * L + 1) * model.dim]
     self.wstream = torch.cuda.Stream(device=device)  # weight-gradient GEMMs run here, filling the tails of the main stream
@@ -194,8 +198,12 @@ class TrainRuntime:
       ops.attn_fwd(ws.qkv[l], ws.attn[l], ws.lse[l], B, T, H, hd, seg_start=seg_start)
       ops.gemm(ws.attn[l], W[pre + 'attn.w_out.weight'], ws.x_mid[l], epilogue=_lib.EPI_RESID_F32, residual=ws.x[l])
       ops.rmsnorm_fwd(ws.x_mid[l], P[pre + 'mlp_norm.weight'], ws.h2[l], ws.rstd2[l], m.eps)
-      # fc1 with the GLU gate applied while the tile is on chip: writes u = [a | z] (saved for backward) and g = silu(a) z
-      ops.gemm(ws.h2[l], W[pre + 'mlp.fc1.weight'], ws.u[l], epilogue=_lib.EPI_BF16_SWIGLU, out2=ws.g[l])
+      if self.act_kind is None:
+        # fc1 with the GLU gate applied while the tile is on chip: writes u = [a | z] (saved for backward), g = silu(a) z
+        ops.gemm(ws.h2[l], W[pre + 'mlp.fc1.weight'], ws.u[l], epilogue=_lib.EPI_BF16_SWIGLU, out2=ws.g[l])
+      else:  # MLP / MLPReluSquared (components.py:31-40, 59-70)
+        ops.gemm(ws.h2[l], W[pre + 'mlp.fc1.weight'], ws.u[l])
+        ops.act_fwd(ws.u[l], ws.g[l], self.act_kind)
       ops.gemm(ws.g[l], W[pre + 'mlp.fc2.weight'], ws.x[l + 1], epilogue=_lib.EPI_RESID_F32, residual=ws.x_mid[l])
     ops.rmsnorm_fwd(ws.x[L], P['out_norm.weight'], ws.hf, ws.rstd_f, m.eps)
     return ws.hf
@@ -330,7 +338,10 @@ class TrainRuntime:
       self._dgrad(dx_b, pre + 'mlp.fc2.weight', ws.dg)
       self._wgrad(dx_b, ws.g[l], pre + 'mlp.fc2.weight', f'dx_b{flip}')
       self._release('du')
-      ops.swiglu_bwd(ws.dg, ws.u[l], ws.du)
+      if self.act_kind is None:
+        ops.swiglu_bwd(ws.dg, ws.u[l], ws.du)
+      else:
+        ops.act_bwd(ws.dg, ws.u[l], ws.du, self.act_kind)
       self._dgrad(ws.du, pre + 'mlp.fc1.weight', ws.dh)
       self._wgrad(ws.du, ws.h2[l], pre + 'mlp.fc1.weight', 'du')
       dx_b = next_dxb()

@@ -77,7 +77,9 @@ class Block(nn.Module):
     # x: fp32 residual stream (bsz, seqlen, dim); both residual adds are fused into the producing GEMM's epilogue
     x = self.attn(self.attn_norm(x), freqs_cis, attn_mask, residual=x)
     u = PF.linear(self.mlp_norm(x), self.mlp.fc1.weight)
-    return PF.linear_residual(PF.swiglu(u), self.mlp.fc2.weight, x)
+    kind = getattr(self.mlp, 'act_kind', None)  # None: GLU; else MLP (silu) / MLPReluSquared (relu^2)
+    h = PF.swiglu(u) if kind is None else PF.activation(u, kind)
+    return PF.linear_residual(h, self.mlp.fc2.weight, x)
 
 
 class Transformer(nn.Module):

@@ -142,6 +142,24 @@ def swiglu_fwd(u, h):
   return h
 
 
+def act_fwd(u, h, kind):
+  """h = act(u): kind = _lib.ACT_SILU (MLP) or _lib.ACT_RELU2 (MLPReluSquared); bf16, same shape."""
+  lib = _lib.load()
+  if u.shape != h.shape:
+    raise ValueError('plainlm_b200.act_fwd: shape mismatch')
+  check(lib.plm_act_fwd(_ptr(u, bf16, 'u'), _ptr(h, bf16, 'h'), u.numel(), kind, _stream()), 'plm_act_fwd')
+  return h
+
+
+def act_bwd(dh, u, du, kind):
+  lib = _lib.load()
+  if not (dh.shape == u.shape == du.shape):
+    raise ValueError('plainlm_b200.act_bwd: shape mismatch')
+  check(lib.plm_act_bwd(_ptr(dh, bf16, 'dh'), _ptr(u, bf16, 'u'), _ptr(du, bf16, 'du'), u.numel(), kind, _stream()),
+        'plm_act_bwd')
+  return du
+
+
 def swiglu_bwd(dh, u, du):
   lib = _lib.load()
   F = dh.shape[-1]
@@ -204,6 +222,21 @@ def signsgd_step(p, g, m, p_bf16, lr, momentum, dampening, weight_decay, first_s
                              _ptr(gnorm_sq, f32, 'gnorm_sq'), float(max_norm or 0.0), _stream()), 'plm_signsgd_step')
 
 
+def nadamw_step(p, g, m, v, p_bf16, lr, beta1, beta2, eps, weight_decay, bc2, c_grad, c_mom, gnorm_sq=None,
+                max_norm=0.0):
+  lib = _lib.load()
+  check(lib.plm_nadamw_step(_ptr(p, f32, 'p'), _ptr(g, f32, 'g'), _ptr(m, f32, 'm'), _ptr(v, f32, 'v'),
+                            _ptr(p_bf16, bf16, 'p_bf16'), p.numel(), lr, beta1, beta2, eps, weight_decay, bc2, c_grad,
+                            c_mom, _ptr(gnorm_sq, f32, 'gnorm_sq'), float(max_norm or 0.0), _stream()), 'plm_nadamw_step')
+
+
+def sgd_step(p, g, buf, p_bf16, lr, momentum, dampening, weight_decay, first_step, gnorm_sq=None, max_norm=0.0):
+  lib = _lib.load()
+  check(lib.plm_sgd_step(_ptr(p, f32, 'p'), _ptr(g, f32, 'g'), _ptr(buf, f32, 'buf'), _ptr(p_bf16, bf16, 'p_bf16'),
+                         p.numel(), lr, momentum, dampening, weight_decay, int(first_step),
+                         _ptr(gnorm_sq, f32, 'gnorm_sq'), float(max_norm or 0.0), _stream()), 'plm_sgd_step')
+
+
 def cast_f32_bf16(src, dst, scale=1.0):
   lib = _lib.load()
   check(lib.plm_cast_f32_bf16(_ptr(src, f32, 'src'), _ptr(dst, bf16, 'dst'), src.numel(), float(scale), _stream()),
@@ -231,7 +264,7 @@ def seg_start_from_lengths(lengths, offsets, seg_start, B, T):
 # `gpu_launches`).  Counting is always on (an integer add per call); event timing only when a Profiler is installed.
 KERNELS_PER_CALL = {
   'gemm': 1, 'attn_fwd': 1, 'attn_bwd': 3, 'rope_qk_': 1, 'rmsnorm_fwd': 1, 'rmsnorm_bwd': 1, 'colsum_accum': 1, 'colsum_accum_batched': 1,
-  'swiglu_fwd': 1, 'swiglu_bwd': 1, 'embed_fwd': 1, 'embed_bwd': 1, 'ce_fwd_bwd': 3, 'sumsq': 2, 'adamw_step': 1,
+  'swiglu_fwd': 1, 'swiglu_bwd': 1, 'act_fwd': 1, 'act_bwd': 1, 'embed_fwd': 1, 'embed_bwd': 1, 'ce_fwd_bwd': 3, 'sumsq': 2, 'adamw_step': 1, 'nadamw_step': 1, 'sgd_step': 1,
   'signsgd_step': 1, 'cast_f32_bf16': 1, 'cast_bf16_f32': 1, 'seg_start_from_lengths': 1,
 }  # fmt: skip
 LAUNCHES = 0

@@ -5,7 +5,7 @@ from .lr_schedule import WarmupCosine, WSD, WarmupConstant, LinearCooldown
 
 
 def intialize_optimizer(param_groups, cfg):
-  """cfg.optim in {'adamw', 'signSGD'} run on the native flat-buffer kernels (reference: init_optim.py:13-21,43-52).
+  """cfg.optim in {'adamw', 'nadamw', 'sgd', 'signSGD'} run on the native flat-buffer kernels (reference: init_optim.py:13-21,43-52).
   The per-group `weight_decay` of `param_groups` overrides the default passed here, as in the reference."""
   if cfg.optim == 'adamw':
     from .adamw import AdamW
@@ -28,9 +28,32 @@ def intialize_optimizer(param_groups, cfg):
       dampening=cfg.dampening,
       weight_decay=cfg.weight_decay,
     )
-  if cfg.optim in ('nadamw', 'sgd', 'sfo_adamw'):
+  if cfg.optim == 'nadamw':
+    from .nadamw import NAdamW
+
+    return NAdamW(
+      param_groups,
+      lr=cfg.lr,
+      betas=[cfg.beta1, cfg.beta2],
+      weight_decay=cfg.weight_decay,
+      decoupled_weight_decay=True,
+      fused=getattr(cfg, 'fused_optim', True),
+      eps=getattr(cfg, 'eps', 1e-8),
+    )
+  if cfg.optim == 'sgd':
+    from .sgd import SGD
+
+    return SGD(
+      param_groups,
+      lr=cfg.lr,
+      momentum=cfg.beta1,
+      dampening=cfg.dampening,
+      weight_decay=cfg.weight_decay,
+    )
+  if cfg.optim == 'sfo_adamw':
     raise NotImplementedError(
-      f"optim '{cfg.optim}' is outside the B200 hot path (SURVEY.md §8(f) N4); supported: 'adamw', 'signSGD'"
+      "optim 'sfo_adamw' needs the third-party schedulefree package (not a kernel of this path; SURVEY.md §8(f) N4); "
+      "supported: 'adamw', 'nadamw', 'sgd', 'signSGD'"
     )
   raise NotImplementedError(f'Not implemented optim: {cfg.optim}.')
 

@@ -12,6 +12,8 @@ from .flat import plan_runs
 
 
 class signSGD(Optimizer):
+  STATE_KEY = 'm'  # reference: optim/signSGD.py state key
+
   def __init__(self, params, lr, momentum=0.0, dampening=0.0, weight_decay=0.1):
     if not 0.0 <= lr:
       raise ValueError(f'Invaid learing rate: {lr}')
@@ -32,17 +34,22 @@ class signSGD(Optimizer):
       bufs = []
       for flat, a, b, ps in runs:
         m = torch.zeros(b - a, device=flat.params.device, dtype=torch.float32)
-        have = ['m' in self.state[p] for p in ps]
+        key_ = self.STATE_KEY
+        have = [key_ in self.state[p] for p in ps]
         if any(have) and not all(have):
           raise RuntimeError('signSGD: partially initialised momentum state inside one flat run')
         for p in ps:
           o, k = p._plm_flat[1] - a, p._plm_flat[2]
-          if 'm' in self.state[p]:
-            m[o : o + k].view(p.shape).copy_(self.state[p]['m'])
+          if key_ in self.state[p]:
+            m[o : o + k].view(p.shape).copy_(self.state[p][key_])
         bufs.append([flat, a, b, ps, m, not all(have) if have else True])
       plan = (key, bufs, loose)
       self._plans[gi] = plan
     return plan
+
+  def _kernel(self, p, g, buf, shadow, group, first, gsq, mx):
+    ops.signsgd_step(p, g, buf, shadow, float(group['lr']), group['momentum'], group['dampening'],
+                     group['weight_decay'], first, gnorm_sq=gsq, max_norm=mx)
 
   @torch.no_grad()
   def step(self, closure=None, grad_clip=None):
@@ -51,25 +58,23 @@ class signSGD(Optimizer):
     mx = grad_clip.max_norm if grad_clip is not None else 0.0
     for gi, group in enumerate(self.param_groups):
       _, bufs, loose = self._plan(gi, group)
-      lr, mu, damp, wd = float(group['lr']), group['momentum'], group['dampening'], group['weight_decay']
+      key_ = self.STATE_KEY
       for rec in bufs:
         flat, a, b, ps, m, first = rec
-        ops.signsgd_step(flat.params[a:b], flat.grads[a:b], m, flat.shadow[a:b], lr, mu, damp, wd, first,
-                         gnorm_sq=gsq, max_norm=mx)
+        self._kernel(flat.params[a:b], flat.grads[a:b], m, flat.shadow[a:b], group, first, gsq, mx)
         if first:
           for p in ps:
             o, k = p._plm_flat[1] - a, p._plm_flat[2]
-            self.state[p]['m'] = m[o : o + k].view(p.shape)
+            self.state[p][key_] = m[o : o + k].view(p.shape)
           rec[5] = False
       for p in loose:
         if p.grad is None:
           continue
         st = self.state[p]
-        first = 'm' not in st
+        first = key_ not in st
         if first:
-          st['m'] = torch.zeros_like(p, memory_format=torch.preserve_format)
-        ops.signsgd_step(p.data, p.grad.contiguous(), st['m'], getattr(p, '_plm_shadow', None), lr, mu, damp, wd,
-                         first, gnorm_sq=gsq, max_norm=mx)
+          st[key_] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        self._kernel(p.data, p.grad.contiguous(), st[key_], getattr(p, '_plm_shadow', None), group, first, gsq, mx)
     return loss
 
   def zero_grad(self, set_to_none=True):

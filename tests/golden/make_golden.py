@@ -305,7 +305,80 @@ def gen_misc_fixture():
   print('misc.json ok')
 
 
+def gen_variants_fixture():
+  """the other MLP classes (models/components.py:31-40, 59-70) through the reference model, and the
+  other optimizers of optim/init_optim.py (sgd through the reference factory; nadamw directly through
+  torch.optim.NAdam(decoupled_weight_decay=True) with the factory's arguments, because the factory also passes
+  `fused=`, which torch 2.11's NAdam rejects — the reference's 'nadamw' branch raises TypeError on this torch)."""
+  from optim import intialize_optimizer
+
+  out = {'mlp': {}, 'optim': {}}
+  B, T, V = 2, TINY['seq_len'], TINY['vocab_size']
+  ids = torch.randint(0, V, (B, T + 1), generator=torch.Generator().manual_seed(12))
+  inputs, targets = ids[:, :T], ids[:, 1 : T + 1].contiguous()
+  out['ids'] = ids
+  for mlp_class in ('mlp', 'mlp_relu_sq'):
+    from models import construct_model
+
+    cfgd = dict(TINY, mlp_class=mlp_class)
+    Cfg = namedtuple('Cfg', cfgd.keys())
+    model, _ = construct_model(Cfg(**cfgd))
+    params = orc.init_params(V, cfgd['d_model'], cfgd['n_layers'], cfgd['n_heads'], seed=8, mlp_class=mlp_class)
+    model.load_state_dict(params, strict=True)
+    rec = {'param_seed': 8, 'param_checksum': checksum(params),
+           'state_dict_shapes': {k: list(v.shape) for k, v in model.state_dict().items()}}
+    for tag in ('fp32', 'bf16'):
+      model.zero_grad(set_to_none=True)
+      if tag == 'fp32':
+        logits = model(inputs, None)
+        loss = torch.nn.CrossEntropyLoss()(logits.view(-1, V), targets.view(-1))
+      else:
+        with torch.autocast('cpu', dtype=torch.bfloat16):
+          logits = model(inputs, None)
+          loss = torch.nn.CrossEntropyLoss()(logits.view(-1, V), targets.view(-1))
+      loss.backward()
+      rec[tag] = {'loss': float(loss), 'logits_head': logits[:, :2, :].float().clone(),
+                  'logits_sum': float(logits.double().sum()),
+                  'grads': grad_summary({k: p.grad for k, p in model.named_parameters()})}
+    out['mlp'][mlp_class] = rec
+  g = torch.Generator().manual_seed(10)
+  for name, cfgd in (('sgd', make_cfg(optim='sgd', lr=1e-2, dampening=0.1)), ('nadamw', make_cfg(optim='nadamw'))):
+    p0 = torch.randn(300, generator=g)
+    n0 = torch.rand(20, generator=g) + 0.5
+    grads = [(torch.randn(300, generator=g) * 2, torch.randn(20, generator=g)) for _ in range(4)]
+    p = torch.nn.Parameter(p0.clone())
+    n = torch.nn.Parameter(n0.clone())
+    groups = [{'params': [p], 'weight_decay': 0.1}, {'params': [n], 'weight_decay': 0.0}]
+    Cfg = namedtuple('Cfg', cfgd.keys())
+    if name == 'sgd':
+      opt = intialize_optimizer(groups, Cfg(**cfgd))
+    else:
+      try:
+        intialize_optimizer([{'params': [torch.nn.Parameter(torch.zeros(1))], 'weight_decay': 0.0}], Cfg(**cfgd))
+        out['nadamw_factory_error'] = None
+      except TypeError as e:
+        out['nadamw_factory_error'] = str(e)
+      opt = torch.optim.NAdam(groups, lr=cfgd['lr'], betas=[cfgd['beta1'], cfgd['beta2']],
+                              weight_decay=cfgd['weight_decay'], decoupled_weight_decay=True, eps=1e-8)
+    snaps = []
+    for i, (gp, gn) in enumerate(grads):
+      for grp in opt.param_groups:
+        grp['lr'] = cfgd['lr'] * (i + 1) / 4
+      p.grad, n.grad = gp.clone(), gn.clone()
+      norm = torch.nn.utils.clip_grad_norm_([p, n], 1.0)
+      opt.step()
+      snaps.append({'p': p.detach().clone(), 'n': n.detach().clone(), 'norm': float(norm)})
+    out['optim'][name] = {'cfg': cfgd, 'p0': p0, 'n0': n0, 'grads': grads, 'snaps': snaps,
+                          'state_keys': sorted(opt.state[p].keys())}
+  torch.save(out, os.path.join(HERE, 'variants.pt'))
+  print('variants.pt', {k: (v['fp32']['loss'], v['bf16']['loss']) for k, v in out['mlp'].items()},
+        {k: v['state_keys'] for k, v in out['optim'].items()}, out['nadamw_factory_error'])
+
+
 if __name__ == '__main__':
+  if len(sys.argv) > 1 and sys.argv[1] == 'variants':
+    gen_variants_fixture()
+    sys.exit(0)
   gen_model_fixture()
   gen_components_fixture()
   gen_docmask_fixture()
@@ -313,3 +386,4 @@ if __name__ == '__main__':
   gen_optim_fixture()
   gen_misc_fixture()
   gen_init_fixture()
+  gen_variants_fixture()

@@ -399,6 +399,58 @@ def test_optimizers_against_reference_fixture(golden_dir):
     assert sorted(sd['state'][0].keys()) == f['state_keys']
 
 
+def test_sgd_nadamw_against_torch_fixture(golden_dir):
+  """the flat SGD / NAdamW kernels against torch.optim.SGD / NAdam(decoupled_weight_decay=True)."""
+  from collections import namedtuple
+  from plainlm_b200.optim import intialize_optimizer
+  from plainlm_b200.optim.flat import GradClip
+  from plainlm_b200 import ops, _lib
+
+  fx = torch.load(os.path.join(golden_dir, 'variants.pt'))['optim']
+  for name in ('sgd', 'nadamw'):
+    f = fx[name]
+    cfgd = dict(f['cfg'])
+    p = torch.nn.Parameter(f['p0'].to(DEV))
+    n = torch.nn.Parameter(f['n0'].to(DEV))
+    opt = intialize_optimizer([{'params': [p], 'weight_decay': 0.1}, {'params': [n], 'weight_decay': 0.0}],
+                              namedtuple('Cfg', cfgd.keys())(**cfgd))
+    ws = torch.empty(_lib.SUMSQ_WORKSPACE, device=DEV)
+    gsq = torch.zeros(1, device=DEV)
+    for i, (gp, gn) in enumerate(f['grads']):
+      for grp in opt.param_groups:
+        grp['lr'] = cfgd['lr'] * (i + 1) / 4
+      p.grad, n.grad = gp.to(DEV), gn.to(DEV)
+      ops.sumsq(p.grad, ws, gsq, accumulate=False)
+      ops.sumsq(n.grad, ws, gsq, accumulate=True)
+      opt.step(grad_clip=GradClip(gsq, 1.0))
+      assert_close(p, f['snaps'][i]['p'], 1e-5, what=f'{name} p step {i}')
+      assert_close(n, f['snaps'][i]['n'], 1e-5, what=f'{name} n step {i}')
+    assert sorted(opt.state[p].keys()) == f['state_keys']
+    sd = opt.state_dict()
+    assert sorted(sd['state'][0].keys()) == f['state_keys']
+    opt.load_state_dict(sd)  # checkpoint round trip keeps the host-side scalars usable
+    p.grad, n.grad = f['grads'][0][0].to(DEV), f['grads'][0][1].to(DEV)
+    opt.step()
+
+
+def test_activation_kernels_against_torch():
+  """plm_act_fwd / plm_act_bwd (MLP: silu, MLPReluSquared: relu^2) against torch on the same bf16 inputs."""
+  ops, _lib = _ops()
+  g = torch.Generator().manual_seed(3)
+  u = (torch.randn(64, 512, generator=g) * 2).to(bf16)
+  dh = torch.randn(64, 512, generator=g).to(bf16)
+  for kind, fn in ((_lib.ACT_SILU, torch.nn.functional.silu), (_lib.ACT_RELU2, lambda x: torch.relu(x).pow(2))):
+    uf = u.float().requires_grad_(True)
+    ref = fn(uf)
+    ref.backward(dh.float())
+    h = torch.empty(64, 512, device=DEV, dtype=bf16)
+    du = torch.empty(64, 512, device=DEV, dtype=bf16)
+    ops.act_fwd(u.to(DEV), h, kind)
+    ops.act_bwd(dh.to(DEV), u.to(DEV), du, kind)
+    assert_close(h, ref.detach(), BF16_RTOL, what=f'act {kind} fwd')
+    assert_close(du, uf.grad, BF16_RTOL, what=f'act {kind} bwd')
+
+
 def test_first_call_from_autograd_thread_in_fresh_process():
   """Regression: the autograd worker thread may have no current CUDA context when a backward kernel is the first thing
   it runs; the C ABI must bind the context that owns its pointers (and never default to device 0)."""

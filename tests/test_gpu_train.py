@@ -87,6 +87,34 @@ def test_fused_step_vs_reference(tiny):
   assert_close(rt.flat.grads, 2 * g1, 1e-3, what='grad accumulation')
 
 
+@pytest.mark.parametrize('mlp_class', ['mlp', 'mlp_relu_sq'])
+def test_mlp_variants_vs_reference(golden_dir, mlp_class):
+  """MLP / MLPReluSquared models — fused runtime step and the modular autograd path against the
+  reference model's loss, logits and gradients (tests/golden/variants.pt)."""
+  from plainlm_b200.models import construct_model
+
+  fx = torch.load(os.path.join(golden_dir, 'variants.pt'))
+  ref = fx['mlp'][mlp_class]
+  model, _ = construct_model(_cfg(**dict(TINY, mlp_class=mlp_class)))
+  model.load_state_dict(orc.init_params(256, 128, 2, 2, seed=ref['param_seed'], mlp_class=mlp_class), strict=True)
+  model = model.to(DEV)
+  rt = model.runtime()
+  T, V = 32, 256
+  ids = fx['ids'].to(DEV)
+  inputs, targets = ids[:, :T].contiguous(), ids[:, 1 : T + 1].contiguous()
+  rt.flat.zero_grads()
+  loss = rt.loss_and_backward(inputs, targets, None, grad_scale=1.0)
+  assert abs(loss.item() - ref['fp32']['loss']) <= 5e-3 * ref['fp32']['loss']
+  _check_grads({k: p.grad for k, p in model.named_parameters()}, ref['bf16']['grads'], 3e-2)
+  _check_grads({k: p.grad for k, p in model.named_parameters()}, ref['fp32']['grads'], 3e-2)
+  fused = rt.flat.grads.clone()
+  rt.flat.zero_grads()
+  logits = model(inputs, None)
+  assert_close(logits[:, :2, :], ref['bf16']['logits_head'], BF16_RTOL, what='logits')
+  torch.nn.CrossEntropyLoss()(logits.float().view(-1, V), targets.view(-1)).backward()
+  assert_close(rt.flat.grads, fused, 3e-2, atol=3e-2 * float(fused.abs().max()), what='modular vs fused grads')
+
+
 def test_fused_step_doc_masked_vs_reference(tiny):
   from plainlm_b200.data_utils import seg_start_from_docs_lengths
 

@@ -154,10 +154,36 @@ def test_tied_embeddings_share_storage():
 
 
 def test_unsupported_variants_say_so():
-  with pytest.raises(NotImplementedError, match='N4'):
-    construct_model(_cfg(**dict(TINY, mlp_class='mlp')))
+  from plainlm_b200.optim import intialize_optimizer
+
   with pytest.raises(NotImplementedError):
     construct_model(_cfg(**dict(TINY, model='pythia-160m')))
+  p = torch.nn.Parameter(torch.zeros(8))
+  with pytest.raises(NotImplementedError, match='schedulefree'):
+    intialize_optimizer([{'params': [p], 'weight_decay': 0.0}],
+                        _cfg(optim='sfo_adamw', lr=1e-3, beta1=0.9, beta2=0.95, weight_decay=0.1))
+
+
+def test_mlp_variants_keep_reference_shapes(golden_dir):
+  """MLP / MLPReluSquared construct with the reference's parameter names and shapes."""
+  fx = torch.load(os.path.join(golden_dir, 'variants.pt'))
+  for mlp_class in ('mlp', 'mlp_relu_sq'):
+    model, _ = construct_model(_cfg(**dict(TINY, mlp_class=mlp_class)))
+    assert {k: list(v.shape) for k, v in model.state_dict().items()} == fx['mlp'][mlp_class]['state_dict_shapes']
+
+
+def test_optimizer_factory_variants():
+  from plainlm_b200.optim import intialize_optimizer
+
+  p = torch.nn.Parameter(torch.zeros(8))
+  base = dict(lr=1e-3, beta1=0.9, beta2=0.95, weight_decay=0.1, dampening=0.1)
+  sgd = intialize_optimizer([{'params': [p], 'weight_decay': 0.0}], _cfg(optim='sgd', **base))
+  assert sorted(sgd.param_groups[0]) == sorted(torch.optim.SGD([p], lr=1e-3, momentum=0.9).param_groups[0].keys() &
+                                               sgd.param_groups[0].keys())
+  assert sgd.param_groups[0]['momentum'] == 0.9 and sgd.param_groups[0]['dampening'] == 0.1
+  nad = intialize_optimizer([{'params': [p], 'weight_decay': 0.0}], _cfg(optim='nadamw', **base))
+  g = nad.param_groups[0]
+  assert g['betas'] == (0.9, 0.95) and g['momentum_decay'] == 4e-3 and g['decoupled_weight_decay'] is True
 
 
 def test_bucket_order_is_backward_completion_order():
@@ -197,7 +223,7 @@ def test_optimizer_factory_and_schedule_coupling(golden_dir):
   opt2 = intialize_optimizer([{'params': [p], 'weight_decay': 0.1}], _train_cfg(optim='signSGD', dampening=0.1))
   assert opt2.param_groups[0]['momentum'] == 0.9 and opt2.param_groups[0]['dampening'] == 0.1
   with pytest.raises(NotImplementedError, match='N4'):
-    intialize_optimizer([{'params': [p]}], _train_cfg(optim='sgd'))
+    intialize_optimizer([{'params': [p]}], _train_cfg(optim='sfo_adamw'))
   assert initialize_scheduler(opt, _train_cfg(scheduler=None)) is None
 
 

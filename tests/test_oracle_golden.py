@@ -186,6 +186,60 @@ def test_optimizers_against_torch_and_reference(golden_dir):
   assert fx['adamw']['state_keys'] == ['exp_avg', 'exp_avg_sq', 'step'] and fx['signsgd']['state_keys'] == ['m']
 
 
+@pytest.mark.parametrize('mlp_class', ['mlp', 'mlp_relu_sq'])
+@pytest.mark.parametrize('tag,rtol', [('fp32', 2e-5), ('bf16', 2e-2)])
+def test_mlp_variants_forward_backward(golden_dir, mlp_class, tag, rtol):
+  """MLP / MLPReluSquared (models/components.py:31-40, 59-70) through the reference model."""
+  fx = torch.load(os.path.join(golden_dir, 'variants.pt'))
+  ref = fx['mlp'][mlp_class]
+  params = orc.init_params(256, 128, 2, 2, seed=ref['param_seed'], mlp_class=mlp_class)
+  chk = float(sum(v.double().abs().sum() for v in params.values()))
+  assert abs(chk - ref['param_checksum']) < 1e-6 * ref['param_checksum']
+  assert {k: list(v.shape) for k, v in params.items()} == ref['state_dict_shapes']
+  p = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+  inputs, targets = orc.split_batch(fx['ids'], 32)
+  logits = orc.forward(p, inputs, 2, None, tag, mlp_class=mlp_class)
+  loss = orc.loss_fn(logits, targets)
+  assert abs(float(loss) - ref[tag]['loss']) <= (1e-5 if tag == 'fp32' else 2e-3) * ref[tag]['loss']
+  assert_close(logits[:, :2, :], ref[tag]['logits_head'], rtol, what='logits')
+  loss.backward()
+  for k, g in ref[tag]['grads'].items():
+    got = p[k].grad
+    assert abs(float(got.double().norm()) - g['norm']) <= rtol * 2 * g['norm'] + 1e-9, k
+    assert_close(got.flatten()[:32], g['head'], rtol * 2, atol=rtol * g['norm'] / got.numel() ** 0.5, what=k)
+
+
+def test_sgd_and_nadamw_against_torch(golden_dir):
+  """optim/init_optim.py:23-41.  The fixture records that the reference's own 'nadamw' branch cannot
+  be built on this torch (it passes fused= to NAdam), so that optimizer is pinned on torch.optim.NAdam directly."""
+  fx = torch.load(os.path.join(golden_dir, 'variants.pt'))
+  assert 'fused' in fx['nadamw_factory_error']
+  for name in ('sgd', 'nadamw'):
+    f = fx['optim'][name]
+    cfg = f['cfg']
+    p, n = f['p0'].clone(), f['n0'].clone()
+    st = {'p': {}, 'n': {}}
+    for i, (gp, gn) in enumerate(f['grads']):
+      lr = cfg['lr'] * (i + 1) / 4
+      gp, gn = gp.clone(), gn.clone()
+      orc.clip_grad_norm_([gp, gn], 1.0)
+      for key, t, g, wd in (('p', p, gp, 0.1), ('n', n, gn, 0.0)):
+        s = st[key]
+        if name == 'sgd':
+          first = not s
+          if first:
+            s['buf'] = torch.zeros_like(t)
+          orc.sgd_step(t, g, s['buf'], first, lr, cfg['beta1'], cfg['dampening'], wd)
+        else:
+          if not s:
+            s['m'], s['v'], s['st'] = torch.zeros_like(t), torch.zeros_like(t), {}
+          orc.nadamw_step(t, g, s['m'], s['v'], s['st'], lr, cfg['beta1'], cfg['beta2'], 1e-8, wd)
+      assert_close(p, f['snaps'][i]['p'], 2e-6, what=f'{name} p step {i}')
+      assert_close(n, f['snaps'][i]['n'], 2e-6, what=f'{name} n step {i}')
+  assert fx['optim']['sgd']['state_keys'] == ['momentum_buffer']
+  assert fx['optim']['nadamw']['state_keys'] == ['exp_avg', 'exp_avg_sq', 'mu_product', 'step']
+
+
 def test_schedule_and_sampler(golden_dir):
   d = json.load(open(os.path.join(golden_dir, 'misc.json')))
   lrs = [orc.warmup_cosine_lr(t, 0.0, 3e-3, 1e-5, 2, 20) for t in range(23)]
