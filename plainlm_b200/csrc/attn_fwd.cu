@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace plm {
@@ -37,7 +38,8 @@ __device__ __forceinline__ float lg2(float x) {
 
 __global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __restrict__ seg_start,
-                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, float scale_log2) {
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, float scale_log2,
+                unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + ATT_TILE_BYTES;
@@ -57,6 +59,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // diagnostics (PLM_ATTN_FWD_TRACE): one CTA stamps clock64() at its phase boundaries for four steady-state tiles
+  const bool tr_on = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == gridDim.z / 2;
+#define AF_TR(slot_)                                                        \
+  do {                                                                      \
+    if (tr_on && it >= 6 && it < 10 && lane == 0) trace[(slot_)] = clock64(); \
+  } while (0)
+  if (tr_on && threadIdx.x == 0) {
+    trace[120] = clock64();
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    trace[122] = gt;
+  }
   const int qt = gridDim.x - 1 - blockIdx.x;  // heavy (late) tiles first
   const int h = blockIdx.y;
   const int b = blockIdx.z;
@@ -105,6 +119,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
         tma_load_2d(sK, &tmQKV, &kv_full[0], d + h * ATT_HD, kr);
         tma_load_2d(sV, &tmQKV, &kv_full[0], 2 * d + h * ATT_HD, kr);
       }
+      // every later K/V tile of this CTA goes to L2 now: the smem ring is only two deep
+      for (int itp = 2; itp < n_it; ++itp) {
+        const int kr = static_cast<int>(static_cast<int64_t>(b) * T + (j_lo + itp) * ATT_BK);
+        tma_prefetch_l2_2d(&tmQKV, d + h * ATT_HD, kr);
+        tma_prefetch_l2_2d(&tmQKV, 2 * d + h * ATT_HD, kr);
+      }
       mbar_wait(q_full, 0);
       // descriptors are built once; per K-step only the 14-bit start-address field advances (tight issue loop)
       const uint64_t q_desc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
@@ -135,10 +155,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
         if (it + 1 < n_it) {
           mbar_wait(&kv_full[st ^ 1], ((it + 1) >> 1) & 1);
           mbar_wait(s_empty, it & 1);
+          AF_TR(64 + (it - 6) * 4 + 0);
           tc_fence_after();
           issue_s(st ^ 1);
+          AF_TR(64 + (it - 6) * 4 + 1);
         }
         mbar_wait(p_full, it & 1);
+        AF_TR(64 + (it - 6) * 4 + 2);
         tc_fence_after();
         const uint64_t v_desc = v_desc0 + st * (ATT_TILE_BYTES >> 4);
 #pragma unroll
@@ -147,6 +170,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
                   (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
         umma_commit(pv_done);
+        AF_TR(64 + (it - 6) * 4 + 3);
         if (it + 2 < n_it) {  // refill this K/V stage for tile it+2 once P·V has drained it
           mbar_wait(&kv_empty[st], (it >> 1) & 1);
           load_kv(it + 2);
@@ -164,105 +188,108 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
 
     for (int it = 0; it < n_it; ++it) {
       const int j = j_lo + it;
+      const bool trw = tr_on && warp == 0;
+#define AF_TRS(k_)                                                                   \
+  do {                                                                               \
+    if (trw && it >= 6 && it < 10 && lane == 0) trace[(it - 6) * 8 + (k_)] = clock64(); \
+  } while (0)
+      AF_TRS(0);
       mbar_wait(s_full, it & 1);
+      AF_TRS(1);
       tc_fence_after();
-      // Two passes over the score tile in TMEM (reads are cheap): pass 1 = row max, pass 2 = exp2 / sum / P store.
-      // The row never sits in registers as a whole, and the softmax scale is folded into the exp2 argument.
+      // The whole score row (128 fp32) is pulled into registers with four back-to-back tcgen05.ld and ONE wait (a load
+      // per pass and per 32-column chunk serialises eight TMEM round trips per tile), and tensor memory is handed back
+      // at once: the next Q K^T runs under this tile's max / exp2 / P-store work.  The softmax scale is folded into the
+      // exp2 argument.
       const int kbase = j * ATT_BK;
       const bool masked = (kbase + ATT_BK - 1 > qi) || (kbase < seg_lo);  // key kj allowed iff seg_lo <= kj <= qi
+      uint32_t t[ATT_BK];
+#pragma unroll
+      for (int c = 0; c < ATT_BK / 32; ++c)
+        tmem_ld32(tS + lane_off + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&t[c * 32]));
+      tmem_ld_wait();
+      AF_TRS(2);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);  // S may be overwritten by the next Q K^T
+      if (masked) {
+#pragma unroll
+        for (int i = 0; i < ATT_BK; ++i) {
+          const int kj = kbase + i;
+          if (kj > qi || kj < seg_lo) t[i] = 0xff800000u;  // -inf
+        }
+      }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < ATT_BK / 32; ++c) {
-        uint32_t t[32];
-        tmem_ld32(tS + lane_off + c * 32, t);
-        tmem_ld_wait();
-        if (masked) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kj = kbase + c * 32 + i;
-            if (kj > qi || kj < seg_lo) t[i] = 0xff800000u;  // -inf
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {  // four independent chains: a single one is 128 dependent FMNMX
-          mx0 = fmaxf(mx0, __uint_as_float(t[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(t[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(t[i + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(t[i + 3]));
-        }
+      for (int i = 0; i < ATT_BK; i += 4) {  // four independent chains: a single one is 128 dependent FMNMX
+        mx0 = fmaxf(mx0, __uint_as_float(t[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(t[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(t[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(t[i + 3]));
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
-
-      // previous P·V must be complete before P smem is overwritten or O is rescaled
-      if (it > 0) {
-        mbar_wait(pv_done, (it - 1) & 1);
-        tc_fence_after();
-      }
+      AF_TRS(3);
+      // running max / lazy rescale decision (registers only; O itself is rescaled after the exp pass, below)
       const bool grow = mx > m_run + 8.0f;
-      if (__any_sync(0xffffffffu, grow)) {
+      const bool any_grow = __any_sync(0xffffffffu, grow);
+      float alpha = 1.0f;
+      if (any_grow) {
         const float m_new = fmaxf(m_run, mx);
-        const float alpha = (m_new == -INFINITY) ? 1.0f : ex2(m_run - m_new);  // m_run = -inf -> 0
+        alpha = (m_new == -INFINITY) ? 1.0f : ex2(m_run - m_new);  // m_run = -inf -> 0
         m_run = m_new;
         l_run *= alpha;
-        if (it > 0) {
-#pragma unroll
-          for (int c = 0; c < ATT_HD / 32; ++c) {
-            uint32_t t[32];
-            tmem_ld32(tO + lane_off + c * 32, t);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
-            tmem_st32(tO + lane_off + c * 32, t);
-          }
-          tmem_st_wait();
-        }
       }
       const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
       const float2 sc2 = make_float2(scale_log2, scale_log2);
       const float2 nm2 = make_float2(-m_use, -m_use);
       float2 ps0 = make_float2(0.f, 0.f), ps1 = make_float2(0.f, 0.f);
-      uint8_t* prow = sP + r * 128;
+      // exp2 pass, in place: P (packed bf16 pairs) overwrites the first half of the score registers, so that nothing
+      // here depends on the previous tile's P·V yet
 #pragma unroll
-      for (int c = 0; c < ATT_BK / 32; ++c) {
-        uint32_t t[32];
-        tmem_ld32(tS + lane_off + c * 32, t);
-        tmem_ld_wait();
-        if (masked) {
+      for (int c16 = 0; c16 < ATT_BK / 8; ++c16) {
+        float2 e[4];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int kj = kbase + c * 32 + i;
-            if (kj > qi || kj < seg_lo) t[i] = 0xff800000u;
-          }
+        for (int i = 0; i < 4; ++i) {
+          const float2 a = __ffma2_rn(
+              make_float2(__uint_as_float(t[c16 * 8 + 2 * i]), __uint_as_float(t[c16 * 8 + 2 * i + 1])), sc2, nm2);
+          e[i] = make_float2(ex2(a.x), ex2(a.y));
         }
+        ps0 = __fadd2_rn(ps0, __fadd2_rn(e[0], e[1]));
+        ps1 = __fadd2_rn(ps1, __fadd2_rn(e[2], e[3]));
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float2 e[4];
+        for (int i = 0; i < 4; ++i) t[c16 * 4 + i] = pack_bf16x2(e[i].x, e[i].y);  // slots < 8*c16: already consumed
+      }
+      AF_TRS(4);
+      // the previous P·V must be complete before O is rescaled or the P tile in smem is overwritten
+      if (it > 0) {
+        mbar_wait(pv_done, (it - 1) & 1);
+        tc_fence_after();
+        if (any_grow) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 a = __ffma2_rn(
-                make_float2(__uint_as_float(t[g * 8 + 2 * i]), __uint_as_float(t[g * 8 + 2 * i + 1])), sc2, nm2);
-            e[i] = make_float2(ex2(a.x), ex2(a.y));
+          for (int c = 0; c < ATT_HD / 16; ++c) {  // 16 columns at a time: the score row is live in registers
+            uint32_t o[16];
+            tmem_ld16(tO + lane_off + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tO + lane_off + c * 16, o);
           }
-          ps0 = __fadd2_rn(ps0, __fadd2_rn(e[0], e[1]));
-          ps1 = __fadd2_rn(ps1, __fadd2_rn(e[2], e[3]));
-          uint4 v;
-          v.x = pack_bf16x2(e[0].x, e[0].y);
-          v.y = pack_bf16x2(e[1].x, e[1].y);
-          v.z = pack_bf16x2(e[2].x, e[2].y);
-          v.w = pack_bf16x2(e[3].x, e[3].y);
-          const int c16 = c * 4 + g;
-          *reinterpret_cast<uint4*>(prow + (c16 >> 3) * ATT_TILE_BYTES + (((c16 & 7) ^ (r & 7)) << 4)) = v;
+          tmem_st_wait();
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty);  // S may be overwritten by the next Q K^T
+      uint8_t* prow = sP + r * 128;
+#pragma unroll
+      for (int c16 = 0; c16 < ATT_BK / 8; ++c16)
+        *reinterpret_cast<uint4*>(prow + (c16 >> 3) * ATT_TILE_BYTES + (((c16 & 7) ^ (r & 7)) << 4)) =
+            make_uint4(t[c16 * 4], t[c16 * 4 + 1], t[c16 * 4 + 2], t[c16 * 4 + 3]);
       const float psum = (ps0.x + ps0.y) + (ps1.x + ps1.y);
       l_run += psum;
+      AF_TRS(5);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      AF_TRS(6);
     }
 
     // ---- epilogue: O / l -> bf16 out[b, t, h, :], lse
@@ -292,6 +319,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
 
   tc_fence_before();
   __syncthreads();
+  if (tr_on && threadIdx.x == 0) {
+    trace[121] = clock64();
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    trace[123] = gt;
+  }
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc<256>(tmem_base);
@@ -324,7 +357,10 @@ extern "C" int plm_attn_fwd(const void* qkv, const int32_t* seg_start, void* out
   if (rc != PLM_OK) return rc;
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(hd));
   dim3 grid((T + ATT_BQ - 1) / ATT_BQ, H, B);
+  // diagnostics: PLM_ATTN_FWD_TRACE = address (hex) of a device buffer of >= 128 uint64 that receives clock64() stamps
+  const char* tr = getenv("PLM_ATTN_FWD_TRACE");
+  unsigned long long* trace = tr ? reinterpret_cast<unsigned long long*>(strtoull(tr, nullptr, 16)) : nullptr;
   attn_fwd_kernel<<<grid, ATT_THREADS, ATT_FWD_SMEM, stream>>>(tm, seg_start, static_cast<__nv_bfloat16*>(out), lse, T,
-                                                               H, scale_log2);
+                                                               H, scale_log2, trace);
   return check_launch("attn_fwd");
 }

@@ -81,6 +81,12 @@ __device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap
       "h"(cta_mask)
       : "memory");
 }
+// Asks the TMA unit to pull a tile into L2 only (no smem, no barrier): hides HBM latency for tiles needed a few steps ahead.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
 // 2-D tile store shared -> global (bulk async group); out-of-bounds parts of the box are clipped by the hardware.
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

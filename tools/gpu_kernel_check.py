@@ -651,6 +651,42 @@ def case_attn_bwd_trace():
   return [{'case': 'timeline', 'events': [f'{t:7d} {n}' for t, n in ev]}]
 
 
+def case_attn_fwd_trace():
+  """clock64 timeline of one attention-forward CTA (PLM_ATTN_FWD_TRACE)."""
+  import torch
+  from plainlm_b200 import ops
+
+  dev = 'cuda'
+  B, T, H, hd = 8, 2048, 16, 64
+  d = H * hd
+  qkv = torch.randn(B * T, 3 * d, device=dev).to(torch.bfloat16)
+  out = torch.empty(B * T, d, device=dev, dtype=torch.bfloat16)
+  lse = torch.empty(B, H, T, device=dev)
+  for _ in range(2):
+    ops.attn_fwd(qkv, out, lse, B, T, H, hd)
+  buf = torch.zeros(128, device=dev, dtype=torch.int64)
+  os.environ['PLM_ATTN_FWD_TRACE'] = hex(buf.data_ptr())
+  ops.attn_fwd(qkv, out, lse, B, T, H, hd)
+  os.environ.pop('PLM_ATTN_FWD_TRACE')
+  torch.cuda.synchronize()
+  v = buf.cpu().tolist()
+  t0 = v[0]
+  ev = []
+  lab_s = ['top', 's_full', 'S in registers', 'max done', 'exp pass done', 'pv_done / rescale / P stored', 'p_full sent', '-']
+  lab_c = ['s_empty seen', 'S(it+1) issued', 'p_full seen', 'PV issued']
+  for itr in range(4):
+    for k in range(8):
+      if v[itr * 8 + k]:
+        ev.append((v[itr * 8 + k] - t0, f'SM it{6 + itr} {lab_s[k]}'))
+    for k in range(4):
+      if v[64 + itr * 4 + k]:
+        ev.append((v[64 + itr * 4 + k] - t0, f'CT it{6 + itr} {lab_c[k]}'))
+  ev.sort()
+  cyc, ns = v[121] - v[120], v[123] - v[122]
+  summary = f'CTA (16 key tiles): {cyc} cycles in {ns} ns = {cyc / max(ns, 1):.3f} GHz; step 6 starts {t0 - v[120]} cycles in'
+  return [{'case': 'timeline', 'summary': summary, 'events': [f'{t:7d} {n}' for t, n in ev]}]
+
+
 def case_attn_perf():
   import torch
   from plainlm_b200 import ops
@@ -729,6 +765,7 @@ CASES['gemm_epi_perf'] = case_gemm_epi_perf
 CASES['gemm_feed_probe'] = case_gemm_feed_probe
 CASES['gemm_n1024_probe'] = case_gemm_n1024_probe
 CASES['attn_bwd_trace'] = case_attn_bwd_trace
+CASES['attn_fwd_trace'] = case_attn_fwd_trace
 CASES['gemm_sustained'] = case_gemm_sustained
 
 
