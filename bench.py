@@ -265,10 +265,12 @@ def run_ours(args):
   prof = ops.Profiler()
   ops.set_profiler(prof)
   engine.use_cuda_graphs = False  # per-kernel events need eager launches
+  os.environ['PLM_NO_SIDE_STREAM'] = '1'  # ... and no overlap: weight-gradient GEMMs back on the main stream
   for m in range(accum):
     dev_step(m)
   summ = prof.summary()
   ops.set_profiler(None)
+  os.environ.pop('PLM_NO_SIDE_STREAM', None)
 
   tokens_per_step = B * T * accum * world
   value = tokens_per_step * K / (ms_value / 1e3)
