@@ -43,11 +43,13 @@ struct GemmParams {
   int n_fastest;  // tile rasterisation: 0 = consecutive tiles walk M (B tile reused), 1 = walk N (A tile reused)
 };
 
-template <int BN>
+// PAIR: the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 (M = 256) per K-step; each CTA's smem then holds
+// only its half of the B tile (N/2 rows), so a stage shrinks from 48 to 32 KB and the ring deepens from 4 to 6.
+template <int BN, bool PAIR = false>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256 && !PAIR) ? 4 : 6;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
@@ -77,13 +79,14 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int rank
   kb1 = min(p.kblocks, kb0 + per);
 }
 
-template <int BN, bool A_K, bool B_K, int CL>
+template <int BN, bool A_K, bool B_K, int CL, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
   static_assert(CL == 1 || CL == 2, "cluster of 1 or 2 CTAs");
+  static_assert(!PAIR || (CL == 2 && BN == 256), "the CTA-pair MMA needs a 2-CTA cluster and 256-wide tiles");
   const int rank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
   const int cluster_id = blockIdx.x / CL;
   const int num_clusters = gridDim.x / CL;
@@ -110,17 +113,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmC2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CL);  // CL = 2: the stage is overwritten in BOTH CTAs, so both must have consumed it
+      // CL = 2: the stage is overwritten in BOTH CTAs, so both CTAs' MMAs must have consumed it (two multicast commits);
+      // PAIR: the leader's single commit covers the pair's MMA
+      mbar_init(&empty[s], PAIR ? 1 : CL);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], GEMM_EPI_WARPS);
+      mbar_init(&tempty[a], PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);  // PAIR: both CTAs' epilogues drain first
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair<Cfg::TMEM_COLS>(tmem_slot);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -138,9 +148,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         decode_work<CL>(p, w, rank, m_blk, n_blk, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], ((p.debug & 8) ? 0 : Cfg::A_BYTES) + ((p.debug & 4) ? 0 : Cfg::B_BYTES));
           uint8_t* a_dst = sA + s * Cfg::A_BYTES;
           uint8_t* b_dst = sB + s * Cfg::B_BYTES;
+          if (PAIR) {
+            // Both CTAs land their A tile and their half of the B tile (N rows [128 rank, +128) of the tile; with the
+            // SwiGLU epilogue: gate rows / up rows) in their OWN smem; all bytes are signalled on the LEADER's barrier,
+            // which its MMA thread waits on.
+            if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+            if (A_K) {
+              tma_load_2d_pair(a_dst, &tmA, &full[s], kb * BK, m_blk * BM);
+            } else {
+#pragma unroll
+              for (int g = 0; g < BM / 64; ++g)
+                tma_load_2d_pair(a_dst + g * (BK * 128), &tmA, &full[s], m_blk * BM + g * 64, kb * BK);
+            }
+            if (B_K) {
+              const int b_row = p.glu_F ? (rank ? p.glu_F : 0) + n_blk * (BN / 2) : n_blk * BN + rank * (BN / 2);
+              tma_load_2d_pair(b_dst, &tmB, &full[s], kb * BK, b_row);
+            } else {
+#pragma unroll
+              for (int g = 0; g < BN / 128; ++g)
+                tma_load_2d_pair(b_dst + g * (BK * 128), &tmB, &full[s], n_blk * BN + (rank * (BN / 128) + g) * 64,
+                                 kb * BK);
+            }
+            if (++s == STAGES) {
+              s = 0;
+              ph ^= 1;
+            }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full[s], ((p.debug & 8) ? 0 : Cfg::A_BYTES) + ((p.debug & 4) ? 0 : Cfg::B_BYTES));
           if (p.debug & 8) {
           } else if (A_K) {
             tma_load_2d(a_dst, &tmA, &full[s], kb * BK, m_blk * BM);
@@ -184,8 +221,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_K ? 0 : 1, B_K ? 0 : 1);
+    if (lane == 0 && (!PAIR || rank == 0)) {  // PAIR: the leader CTA issues for both
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN, A_K ? 0 : 1, B_K ? 0 : 1);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -208,9 +245,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                        : make_smem_desc_sw128(a_addr + k * 2048, BK * 128, 1024);
             const uint64_t bdesc = B_K ? make_smem_desc_sw128(b_addr + k * 32, 16, 1024)
                                        : make_smem_desc_sw128(b_addr + k * 2048, BK * 128, 1024);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR)
+              umma_ss_pair(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else
+              umma_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          if (CL == 2)
+          if (PAIR)
+            umma_commit_pair(&empty[s]);
+          else if (CL == 2)
             umma_commit_mc(&empty[s], 0x3);
           else
             umma_commit(&empty[s]);
@@ -219,7 +261,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             ph ^= 1;
           }
         }
-        umma_commit(&tfull[a]);
+        if (PAIR)
+          umma_commit_pair(&tfull[a]);  // both CTAs' epilogues read their own 128 rows of the accumulator
+        else
+          umma_commit(&tfull[a]);
       }
     }
   } else {
@@ -345,7 +390,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (j == BN / 128 - 1) {  // last read of this accumulator: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[a]);
+            if (lane == 0) {
+              if (PAIR)
+                mbar_arrive_cluster(&tempty[a], 0);  // the leader's MMA thread owns the pair's accumulators
+              else
+                mbar_arrive(&tempty[a]);
+            }
           }
           emit(oa, &tmC, gate_col0 + j * 64);
           emit(oz, &tmC, p.glu_F + gate_col0 + j * 64);
@@ -399,7 +449,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (c == n_chunks - 1) {  // last read of this accumulator: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[a]);
+            if (lane == 0) {
+              if (PAIR)
+                mbar_arrive_cluster(&tempty[a], 0);  // the leader's MMA thread owns the pair's accumulators
+              else
+                mbar_arrive(&tempty[a]);
+            }
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -430,7 +485,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (sc == n_sub - 1) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[a]);
+            if (lane == 0) {
+              if (PAIR)
+                mbar_arrive_cluster(&tempty[a], 0);  // the leader's MMA thread owns the pair's accumulators
+              else
+                mbar_arrive(&tempty[a]);
+            }
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -471,18 +531,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (CL == 2) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR)
+      tmem_dealloc_pair<Cfg::TMEM_COLS>(tmem_base);
+    else
+      tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
-template <int BN, bool A_K, bool B_K, int CL>
+template <int BN, bool A_K, bool B_K, int CL, bool PAIR = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                        const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, PAIR>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_kernel<BN, A_K, B_K, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_kernel<BN, A_K, B_K, CL, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return fail(PLM_ERR_CUDA, "gemm smem attribute: %s", cudaGetErrorString(attr_err));
@@ -501,7 +564,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_K, B_K, CL>, tmA, tmB, tmC, tmC2, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_kernel<BN, A_K, B_K, CL, PAIR>, tmA, tmB, tmC, tmC2, p);
   if (e != cudaSuccess) return fail(PLM_ERR_CUDA, "gemm_kernel launch: %s", cudaGetErrorString(e));
   return check_launch("gemm_kernel");
 }
@@ -645,6 +708,15 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   if (a_k && !b_k) return launch_gemm<BN_, true, false, CL_>(tmA, tmB, tmC, tmC2, p, stream);    \
   if (!a_k && b_k) return launch_gemm<BN_, false, true, CL_>(tmA, tmB, tmC, tmC2, p, stream);    \
   return launch_gemm<BN_, false, false, CL_>(tmA, tmB, tmC, tmC2, p, stream);
+  // CTA-pair MMA (tcgen05.mma.cta_group::2) for every clustered launch; PLM_GEMM_PAIR=0 falls back to two
+  // cta_group::1 MMAs sharing a multicast B tile
+  const bool pair = cl == 2 && bn == 256 && env_int("PLM_GEMM_PAIR", 1) != 0;
+  if (pair) {
+    if (a_k && b_k) return launch_gemm<256, true, true, 2, true>(tmA, tmB, tmC, tmC2, p, stream);
+    if (a_k && !b_k) return launch_gemm<256, true, false, 2, true>(tmA, tmB, tmC, tmC2, p, stream);
+    if (!a_k && b_k) return launch_gemm<256, false, true, 2, true>(tmA, tmB, tmC, tmC2, p, stream);
+    return launch_gemm<256, false, false, 2, true>(tmA, tmB, tmC, tmC2, p, stream);
+  }
   if (bn == 256 && cl == 2) {
     PLM_DISPATCH(256, 2)
   } else if (bn == 256) {
