@@ -39,7 +39,8 @@ struct GemmParams {
   int glu_F;  // PLM_EPI_BF16_SWIGLU: F = N/2; tile n covers gate columns [128n, 128n+128) and up columns F + the same
   int num_m, num_n, kblocks;
   int debug;      // diagnostics only (PLM_GEMM_DEBUG): 1 = skip epilogue operand loads, 2 = skip stores,
-                  // 4 = skip B tile loads, 8 = skip A tile loads (results are then garbage; timing experiments only)
+                  // 4 = skip B tile loads, 8 = skip A tile loads, 16 = skip only the epilogue's global operand loads
+                  // (results are then garbage; timing experiments only)
   int n_fastest;  // tile rasterisation: 0 = consecutive tiles walk M (B tile reused), 1 = walk N (A tile reused)
 };
 
@@ -303,6 +304,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       // coalesced fetch of sub-chunk `sc`'s global operand: dst[j] = piece `piece` of row lrow0 + 4j
       auto fetch_aux = [&](float4(&dst)[8], int sc) {
+        if (p.debug & 16) return;  // timing experiment: keep the staging + math, drop the global loads
         const int64_t col0 = tile_col0 + sc * 32;
         if (is_resid) {
           const int64_t colp = col0 + piece * 4;

@@ -479,7 +479,7 @@ def case_gemm_epi_perf():
     ('swiglu alone', lambda: ops.swiglu_fwd(u, g), 2.0 * M * d * 2 * F),
   ]
   results = []
-  for dbg in (0, 1, 2, 3):
+  for dbg in (0, 1, 2, 3, 16):
     os.environ['PLM_GEMM_DEBUG'] = str(dbg)
     for n, fn, fl in cases:
       ms = _time(fn, 10)
