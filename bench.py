@@ -262,7 +262,7 @@ def run_ours(args):
   ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
   # ---------------------------------------------------------------- one instrumented step: per-kernel CUDA events
-  prof = ops.Profiler()
+  prof = ops.Profiler(sync=bool(os.environ.get('PLM_BENCH_SYNC_PROFILE')))
   ops.set_profiler(prof)
   engine.use_cuda_graphs = False  # per-kernel events need eager launches
   os.environ['PLM_NO_SIDE_STREAM'] = '1'  # ... and no overlap: weight-gradient GEMMs back on the main stream
@@ -285,6 +285,14 @@ def run_ours(args):
       rate = work * cnt / (ms / 1e3) / (1e12 if kind == 'tensor' else 1e9)
       rows.append(f'{name:22s} {str(tag):44s} calls {cnt:4d}  total {ms:8.3f} ms  avg {ms / cnt * 1e3:8.1f} us  '
                   f'{rate:8.1f} {"TF/s" if kind == "tensor" else "GB/s"}')
+    torch.cuda.synchronize()
+    per = {}
+    for name, tag, e0, e1 in prof.records:
+      per.setdefault(name, []).append(e0.elapsed_time(e1) * 1e3)
+    for name, ts in per.items():
+      srt = sorted(ts)
+      rows.append(f'{name:22s} per-call us: min {srt[0]:.1f} median {srt[len(srt) // 2]:.1f} max {srt[-1]:.1f}; '
+                  f'largest: {[round(x) for x in srt[-6:]]}; first calls: {[round(x) for x in ts[:4]]}')
     with open(os.environ['PLM_BENCH_DETAIL'], 'w') as f:
       f.write('\n'.join(rows) + '\n')
 

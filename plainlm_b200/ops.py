@@ -273,16 +273,21 @@ LAUNCHES = 0
 class Profiler:
   """Records (op name, tag, cuda start/end events) for every op call while installed."""
 
-  def __init__(self):
+  def __init__(self, sync=False):
     self.records = []
+    self.sync = sync  # drain the device before every op: each interval then holds exactly one op (plus launch latency)
 
   def summary(self):
     torch.cuda.synchronize()
-    out = {}
+    per = {}
     for name, tag, e0, e1 in self.records:
-      rec = out.setdefault((name, tag), [0, 0.0])
-      rec[0] += 1
-      rec[1] += e0.elapsed_time(e1)
+      per.setdefault((name, tag), []).append(e0.elapsed_time(e1))
+    # total = median x calls: a host hiccup (GC, a clock-sampling subprocess) while the device queue is empty lands in
+    # whichever interval happens to be open and would otherwise be charged to that kernel
+    out = {}
+    for key, ts in per.items():
+      ts.sort()
+      out[key] = [len(ts), ts[len(ts) // 2] * len(ts)]
     return out
 
 
@@ -314,6 +319,8 @@ def _instrument(name, fn):
     if prof is None:
       return fn(*args, **kwargs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if prof.sync:
+      torch.cuda.synchronize()
     e0.record()
     out = fn(*args, **kwargs)
     e1.record()
