@@ -3,11 +3,12 @@
 // One CTA per (128-query tile, head, batch); 160 threads:
 //   warps 0..3  softmax: thread r owns query row r (TMEM lane r) — row max / sum need no shuffles
 //   warp 4      control: one thread issues the TMA loads (Q once, K/V double-buffered) and all tcgen05.mma
-// Per 128-key tile:  S = Q K^T  (TMEM cols 0..127)  ->  softmax in registers  ->  P (bf16) to swizzled smem
-//                    ->  O += P V  (TMEM cols 128..191, V consumed MN-major straight from its TMA box).
+// Per 128-key tile:  S = Q K^T  (TMEM cols 0..127)  ->  softmax in registers  ->  P (bf16 pairs) to TMEM cols 192..255
+//                    ->  O += P V  (TMEM cols 128..191; A = P read from tensor memory, V consumed MN-major straight
+//                        from its TMA box).
 // O stays in TMEM for the whole row of tiles; it is rescaled only when the running max grows by more than 2^8
 // (lazy rescale), so the common path never round-trips O through registers.  Two CTAs are resident per SM
-// (112 KB smem, 256 TMEM columns each): one CTA's softmax overlaps the other's MMAs.
+// (80 KB smem, 256 TMEM columns each): one CTA's softmax overlaps the other's MMAs.
 // Document masking never touches a dense mask: a row attends keys in [seg_start[row], row]; key tiles entirely
 // before the tile's first document are skipped.
 #include "common.cuh"
@@ -23,12 +24,17 @@ constexpr int ATT_BK = 128;   // keys per tile
 constexpr int ATT_HD = 64;    // head dim
 constexpr int ATT_THREADS = 160;
 constexpr int ATT_TILE_BYTES = ATT_BK * ATT_HD * 2;  // 16 KB
-constexpr int ATT_FWD_SMEM = ATT_TILE_BYTES * (1 + 2 + 2 + 2) + 128;  // Q, K x2, V x2, P (2 blocks) + barriers
+constexpr int ATT_FWD_SMEM = ATT_TILE_BYTES * (1 + 2 + 2) + 128;  // Q, K x2, V x2 + barriers (P lives in tensor memory)
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
 }
 __device__ __forceinline__ float lg2(float x) {
   float y;
@@ -44,8 +50,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
   uint8_t* sQ = smem;
   uint8_t* sK = smem + ATT_TILE_BYTES;
   uint8_t* sV = smem + 3 * ATT_TILE_BYTES;
-  uint8_t* sP = smem + 5 * ATT_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * ATT_TILE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * ATT_TILE_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
@@ -105,6 +110,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base;
   const uint32_t tO = tmem_base + 128;
+  const uint32_t tP = tmem_base + 192;  // P as packed bf16 pairs: lane = query row, 64 columns = 128 keys
 
   if (warp == 4) {
     if (lane == 0) {
@@ -130,7 +136,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
       const uint64_t q_desc = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t k_desc0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t v_desc0 = make_smem_desc_sw128(smem_u32(sV), ATT_TILE_BYTES, 1024);  // MN-major view
-      const uint64_t p_desc = make_smem_desc_sw128(smem_u32(sP), 16, 1024);
       auto issue_s = [&](int st) {
         const uint64_t k_desc = k_desc0 + st * (ATT_TILE_BYTES >> 4);
 #pragma unroll
@@ -166,8 +171,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
         const uint64_t v_desc = v_desc0 + st * (ATT_TILE_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < ATT_BK / 16; ++k)
-          umma_ss(tO, p_desc + ((k >> 2) * ATT_TILE_BYTES + (k & 3) * 32) / 16, v_desc + k * (2048 >> 4), idesc_o,
-                  (it > 0 || k > 0) ? 1u : 0u);
+          umma_ts(tO, tP + k * 8, v_desc + k * (2048 >> 4), idesc_o, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
         umma_commit(pv_done);
         AF_TR(64 + (it - 6) * 4 + 3);
@@ -221,11 +225,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < ATT_BK; i += 4) {  // four independent chains: a single one is 128 dependent FMNMX
-        mx0 = fmaxf(mx0, __uint_as_float(t[i]));
-        mx1 = fmaxf(mx1, __uint_as_float(t[i + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(t[i + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(t[i + 3]));
+      for (int i = 0; i < ATT_BK; i += 8) {  // four independent chains of 3-input maxima (FMNMX3): 64 instructions
+        mx0 = max3f(mx0, __uint_as_float(t[i]), __uint_as_float(t[i + 1]));
+        mx1 = max3f(mx1, __uint_as_float(t[i + 2]), __uint_as_float(t[i + 3]));
+        mx2 = max3f(mx2, __uint_as_float(t[i + 4]), __uint_as_float(t[i + 5]));
+        mx3 = max3f(mx3, __uint_as_float(t[i + 6]), __uint_as_float(t[i + 7]));
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
       AF_TRS(3);
@@ -277,15 +281,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __rest
           tmem_st_wait();
         }
       }
-      uint8_t* prow = sP + r * 128;
-#pragma unroll
-      for (int c16 = 0; c16 < ATT_BK / 8; ++c16)
-        *reinterpret_cast<uint4*>(prow + (c16 >> 3) * ATT_TILE_BYTES + (((c16 & 7) ^ (r & 7)) << 4)) =
-            make_uint4(t[c16 * 4], t[c16 * 4 + 1], t[c16 * 4 + 2], t[c16 * 4 + 3]);
+      // P goes to tensor memory (A operand of the P·V MMA, read in place): no smem round trip — hd = 64 MMAs are
+      // shared-memory-bandwidth bound, and the P tile was 44 % of this kernel's smem traffic
+      tmem_st32(tP + lane_off, *reinterpret_cast<const uint32_t(*)[32]>(&t[0]));
+      tmem_st32(tP + lane_off + 32, *reinterpret_cast<const uint32_t(*)[32]>(&t[32]));
+      tmem_st_wait();
       const float psum = (ps0.x + ps0.y) + (ps1.x + ps1.y);
       l_run += psum;
       AF_TRS(5);
-      fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);

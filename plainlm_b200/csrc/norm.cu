@@ -76,19 +76,22 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
       xv[i] = __ldcs(xr + i * 32 + lane);
       dv[i] = __ldcs(dyr + i * 32 + lane);
     }
-    {  // pull the NEXT row of this warp into L2 while this one is reduced: the kernel is latency-bound, not bandwidth-bound
+    {  // pull the NEXT row of this warp into L2 while this one is reduced: the kernel is latency-bound, not
+       // bandwidth-bound.  One 128-byte line per lane: a single instruction covers 4 KB.
       const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * NORM_WARPS;
       if (nrow < rows) {
 #pragma unroll
-        for (int i = 0; i < VPL; i += 2)  // one prefetch per lane covers 16 B; lanes 0..31 cover 512 B = 4 lines
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(x + nrow * D + (i * 32 + lane) * 4));
+        for (int i = 0; i < (D * 4 + 4095) / 4096; ++i) {
+          const int off = (i * 32 + lane) * 32;  // floats
+          if (off < D) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(x + nrow * D + off));
+            if (dx_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(dx_in + nrow * D + off));
+          }
+        }
 #pragma unroll
-        for (int i = 0; i < VPL; i += 4)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(dy + nrow * D + (i * 32 + lane) * 4));
-        if (dx_in) {
-#pragma unroll
-          for (int i = 0; i < VPL; i += 2)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(dx_in + nrow * D + (i * 32 + lane) * 4));
+        for (int i = 0; i < (D * 2 + 4095) / 4096; ++i) {
+          const int off = (i * 32 + lane) * 64;  // bf16 elements
+          if (off < D) asm volatile("prefetch.global.L2 [%0];" ::"l"(dy + nrow * D + off));
         }
       }
     }
