@@ -42,6 +42,13 @@ def test_library_exports_every_declared_symbol():
   assert _lib.load().plm_abi_version() == 2
 
 
+def test_graft_entry_build_passes():
+  """The driver's "does it build" check: incremental make + ABI version + every symbol (no GPU needed)."""
+  import __graft_entry__ as g
+
+  g.build()
+
+
 def test_no_torch_types_in_abi():
   src = open(os.path.join(ROOT, 'include', 'plainlm_b200.h')).read()
   code = re.sub(r'/\*.*?\*/', '', src, flags=re.S)  # comments may mention PyTorch; declarations may not
