@@ -1,15 +1,15 @@
 // RMSNorm forward / backward (models/components.py:16-28) as single-pass bandwidth kernels.
 // One warp owns one row; the row lives in registers (d = 128 * VPL, float4 per lane per 128 columns), reductions are
 // warp shuffles, every global access is a 128-bit vector.  Forward: 4 B/elt read + 2 B/elt write.
-// Backward: reads dy (2) + x (4) [+ dx_in (4)], writes dx (4) [+ bf16 copy (2)]; dw partial sums stay in registers
-// across the rows a warp visits and are reduced once per block.
+// Backward: reads dy (2) + x (4) [+ dx_in (4)] through a cp.async shared-memory ring, writes dx (4) [+ bf16 copy (2)];
+// dw partial sums stay in registers across the rows a warp visits and are reduced once per block.
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace plm {
 
 constexpr int NORM_WARPS = 8;
-constexpr int NORM_BWD_MAX_BLOCKS = 296;  // 2 per SM x 8 warps resident; each warp prefetches its next row into L2
+constexpr int NORM_BWD_MAX_BLOCKS = 148;  // rmsnorm_bwd: one persistent block per SM
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -48,52 +48,89 @@ rmsnorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, __n
   }
 }
 
-// Backward.  A warp owns TWO half-rows at a time?  No: one row per warp, but the row is streamed in two register-light
-// passes — pass 1 (dot product) keeps only packed dy (bf16) and x in registers, pass 2 recomputes from them.  dw partials
-// live in shared memory (one fp32 per column per warp-slot), not registers, which is what lets 4 blocks stay resident.
+// Backward.  One row per warp and step, one persistent block (up to 6 warps) per SM.  The register-resident version of this
+// kernel was latency-bound (ncu: 79 % of stall cycles long-scoreboard, 4.2 TB/s): what a warp can have in flight was
+// capped by the registers that receive its loads.  Here every warp streams its rows through a private shared-memory ring
+// with cp.async (x, dx_in, dy of the next STAGES-1 rows are in flight while one row is computed), so ~160 of the SM's
+// 227 KB of shared memory are outstanding loads.
+// Measured at d = 1024 (16384 rows): 4 warps x 5 stages 53 us, 6 x 3 47.5 us, 7 x 3 47 us, 8 x 2 48 us
+// (register-resident predecessor: 61 us).
+constexpr int NORM_BWD_SMEM_BUDGET = 220 * 1024;
 template <int VPL>
-__global__ void __launch_bounds__(NORM_WARPS * 32, (VPL <= 8) ? 2 : 1)
+struct NormBwdCfg {
+  static constexpr int D = VPL * 128;
+  static constexpr int ROW_BYTES = D * 10;  // x fp32 | dx_in fp32 | dy bf16
+  static constexpr int WFIT = NORM_BWD_SMEM_BUDGET / (2 * ROW_BYTES);  // warps that fit with a 2-deep ring
+  static constexpr int WARPS = WFIT > 6 ? 6 : WFIT;
+  static constexpr int FIT = NORM_BWD_SMEM_BUDGET / (WARPS * ROW_BYTES);
+  static constexpr int STAGES = FIT > 8 ? 8 : FIT;
+  static constexpr int SMEM = WARPS * STAGES * ROW_BYTES;
+  static_assert(WARPS >= 1 && STAGES >= 2 && SMEM <= 227 * 1024, "rmsnorm_bwd ring does not fit");
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(NormBwdCfg<VPL>::WARPS * 32, 1)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                    const float* __restrict__ rstd, const float* dx_in, float* dx_out,
                    __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dw_partial, int64_t rows) {
-  constexpr int D = VPL * 128;
-  __shared__ float4 red[NORM_WARPS][32];
+  using Cfg = NormBwdCfg<VPL>;
+  constexpr int D = Cfg::D;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int NORM_BWD_WARPS = Cfg::WARPS;
+  extern __shared__ __align__(16) uint8_t ring[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  uint8_t* wring = ring + warp * (STAGES * Cfg::ROW_BYTES);
   const float4* wr = reinterpret_cast<const float4*>(w);
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * NORM_BWD_WARPS + warp;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * NORM_BWD_WARPS;
   float4 dw[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) dw[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * NORM_WARPS + warp; row < rows;
-       row += static_cast<int64_t>(gridDim.x) * NORM_WARPS) {
-    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
-    const uint2* dyr = reinterpret_cast<const uint2*>(dy + row * D);
+
+  // one cp.async group per row (empty past the end, so the group arithmetic stays uniform)
+  auto issue = [&](int64_t row, int st) {
+    if (row < rows) {
+      uint8_t* base = wring + st * Cfg::ROW_BYTES;
+      const float4* xs = reinterpret_cast<const float4*>(x + row * D);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) cp_async16(base + (i * 32 + lane) * 16, xs + i * 32 + lane);
+      if (dx_in) {
+        const float4* ds = reinterpret_cast<const float4*>(dx_in + row * D);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) cp_async16(base + D * 4 + (i * 32 + lane) * 16, ds + i * 32 + lane);
+      }
+      const uint4* ys = reinterpret_cast<const uint4*>(dy + row * D);
+      for (int pc = lane; pc < VPL * 16; pc += 32) cp_async16(base + D * 8 + pc * 16, ys + pc);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) issue(row0 + s * stride, s);
+
+  int st = 0;
+  for (int64_t row = row0; row < rows; row += stride) {
+    __syncwarp();  // every lane is done with the stage that is refilled now (it was consumed one step ago)
+    issue(row + (STAGES - 1) * stride, (st + STAGES - 1) % STAGES);
+    cp_async_wait<STAGES - 1>();  // this row's group has landed
+    __syncwarp();                 // ... for every lane (dy pieces are copied and read by different lanes)
+    const uint8_t* base = wring + st * Cfg::ROW_BYTES;
     const float r = rstd[row];
     float4 xv[VPL];
     uint2 dv[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-      xv[i] = __ldcs(xr + i * 32 + lane);
-      dv[i] = __ldcs(dyr + i * 32 + lane);
-    }
-    {  // pull the NEXT row of this warp into L2 while this one is reduced: the kernel is latency-bound, not
-       // bandwidth-bound.  One 128-byte line per lane: a single instruction covers 4 KB.
-      const int64_t nrow = row + static_cast<int64_t>(gridDim.x) * NORM_WARPS;
-      if (nrow < rows) {
-#pragma unroll
-        for (int i = 0; i < (D * 4 + 4095) / 4096; ++i) {
-          const int off = (i * 32 + lane) * 32;  // floats
-          if (off < D) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(x + nrow * D + off));
-            if (dx_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(dx_in + nrow * D + off));
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < (D * 2 + 4095) / 4096; ++i) {
-          const int off = (i * 32 + lane) * 64;  // bf16 elements
-          if (off < D) asm volatile("prefetch.global.L2 [%0];" ::"l"(dy + nrow * D + off));
-        }
-      }
+      xv[i] = *reinterpret_cast<const float4*>(base + (i * 32 + lane) * 16);
+      dv[i] = *reinterpret_cast<const uint2*>(base + D * 8 + (i * 32 + lane) * 8);
     }
     float dot = 0.f;
 #pragma unroll
@@ -104,7 +141,6 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
     }
     dot = warp_sum(dot) * r * (1.0f / D);  // mean_j (dy_j w_j xhat_j)
     float4* dxo = reinterpret_cast<float4*>(dx_out + row * D);
-    const float4* dxi = reinterpret_cast<const float4*>(dx_in ? dx_in + row * D : nullptr);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       const float4 ww = __ldg(wr + i * 32 + lane);
@@ -120,7 +156,7 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
       o.z = r * (d2 * ww.z - h2 * dot);
       o.w = r * (d3 * ww.w - h3 * dot);
       if (dx_in) {
-        const float4 a = __ldcs(dxi + i * 32 + lane);
+        const float4 a = *reinterpret_cast<const float4*>(base + D * 4 + (i * 32 + lane) * 16);
         o.x += a.x;
         o.y += a.y;
         o.z += a.z;
@@ -128,32 +164,33 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
       }
       __stcs(dxo + i * 32 + lane, o);
       if (dx_bf16) {
-        uint2 b;
-        b.x = pack_bf16x2(o.x, o.y);
-        b.y = pack_bf16x2(o.z, o.w);
-        reinterpret_cast<uint2*>(dx_bf16 + row * D)[i * 32 + lane] = b;
+        uint2 bq;
+        bq.x = pack_bf16x2(o.x, o.y);
+        bq.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(dx_bf16 + row * D)[i * 32 + lane] = bq;
       }
     }
+    st = (st + 1) % STAGES;
   }
-  // block reduction of the dw partials, fixed order (warp 0..7) => deterministic
+  cp_async_wait<0>();
+  // block reduction of the dw partials through the (now idle) ring, fixed order (warp 0..3) => deterministic
+  __syncthreads();
+  float4* red = reinterpret_cast<float4*>(ring);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) red[warp * (D / 4) + i * 32 + lane] = dw[i];
+  __syncthreads();
   float4* out = reinterpret_cast<float4*>(dw_partial + static_cast<int64_t>(blockIdx.x) * D);
+  for (int c = threadIdx.x; c < D / 4; c += NORM_BWD_WARPS * 32) {
+    float4 sacc = red[c];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    red[warp][lane] = dw[i];
-    __syncthreads();
-    if (warp == 0) {
-      float4 s = red[0][lane];
-#pragma unroll
-      for (int k = 1; k < NORM_WARPS; ++k) {
-        const float4 t = red[k][lane];
-        s.x += t.x;
-        s.y += t.y;
-        s.z += t.z;
-        s.w += t.w;
-      }
-      out[i * 32 + lane] = s;
+    for (int k = 1; k < NORM_BWD_WARPS; ++k) {
+      const float4 t = red[k * (D / 4) + c];
+      sacc.x += t.x;
+      sacc.y += t.y;
+      sacc.z += t.z;
+      sacc.w += t.w;
     }
-    __syncthreads();
+    out[c] = sacc;
   }
 }
 
@@ -185,8 +222,8 @@ colsum_accum_kernel(const float* __restrict__ partial, float* __restrict__ dw, i
   }
 }
 
-static int norm_bwd_blocks(int64_t rows) {
-  int64_t b = (rows + NORM_WARPS - 1) / NORM_WARPS;
+static int norm_bwd_blocks(int64_t rows) {  // independent of d: the caller sizes dw_partial from it
+  int64_t b = (rows + 3) / 4;
   if (b > NORM_BWD_MAX_BLOCKS) b = NORM_BWD_MAX_BLOCKS;
   if (b < 1) b = 1;
   return static_cast<int>(b);
@@ -241,7 +278,13 @@ int plm_rmsnorm_bwd(const void* dy_bf16, const float* x, const float* w, const f
               "rmsnorm_bwd: misaligned pointer");
   if (d % 128 != 0) return fail(PLM_ERR_UNSUPPORTED, "rmsnorm: d=%d must be a multiple of 128", d);
   const int blocks = norm_bwd_blocks(rows);
-  PLM_VPL_SWITCH(d / 128, (rmsnorm_bwd_kernel<V><<<blocks, NORM_WARPS * 32, 0, stream>>>(
+  {
+    cudaError_t e = cudaSuccess;
+    PLM_VPL_SWITCH(d / 128, (e = cudaFuncSetAttribute(rmsnorm_bwd_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      NormBwdCfg<V>::SMEM)));
+    if (e != cudaSuccess) return fail(PLM_ERR_CUDA, "rmsnorm_bwd smem attribute: %s", cudaGetErrorString(e));
+  }
+  PLM_VPL_SWITCH(d / 128, (rmsnorm_bwd_kernel<V><<<blocks, NormBwdCfg<V>::WARPS * 32, NormBwdCfg<V>::SMEM, stream>>>(
                               static_cast<const __nv_bfloat16*>(dy_bf16), x, w, rstd, dx_in, dx_out,
                               static_cast<__nv_bfloat16*>(dx_out_bf16), dw_partial, rows)));
   return check_launch("rmsnorm_bwd");
