@@ -55,7 +55,8 @@ int plm_device_check(void);
  *                       fp32 (cos, sin); position of row r is r % rope_T; pair index of column c is (c % head_dim)/2)
  *   PLM_EPI_F32         C (fp32)  = acc
  *   PLM_EPI_RESID_F32   C (fp32)  = R (fp32, same ld as C) + acc         (models/transformer.py:81-82 residual add)
- *   PLM_EPI_ATOMIC_F32  C (fp32) += acc with red.global.add (split-K capable; fp32 .grad accumulation)
+ *   PLM_EPI_ATOMIC_F32  C (fp32) += acc through TMA bulk reduce-adds performed at L2 (split-K capable; fp32 .grad
+ *                       accumulation across micro-steps)
  *   PLM_EPI_BF16_SWIGLU C (bf16)  = acc  AND  C2 (bf16 [M, N/2], ld = ldc2) = silu(C[:, :N/2]) * C[:, N/2:]
  *                       (models/components.py:55-56: the GLU gate applied to fc1's output u = [a | z] while the tile is
  *                       still on chip; silu is evaluated on the bf16-rounded a, z exactly like plm_swiglu_fwd).

@@ -1,13 +1,14 @@
 // tcgen05 GEMM for every nn.Linear of the plainLM train step (models/transformer.py:42,67,114;
 // models/components.py:55-56) — forward, dgrad and wgrad — replacing the cuBLASLt calls PyTorch makes under autocast.
 //
-// One persistent CTA per SM, 320 threads:
+// One persistent CTA per SM, 192 threads; launched as 2-CTA clusters whenever there is more than one M block:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled boxes, STAGES-deep mbarrier ring)
-//   warp 1      MMA issuer     (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM; owns TMEM alloc/dealloc)
-//   warps 2..9  epilogue       (tcgen05.ld 32x32b, one accumulator row per thread, two warps per TMEM lane quarter each
-//               draining half of the columns; fused epilogues with their global operands prefetched; direct stores)
+//   warp 1      MMA issuer     (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM; owns TMEM alloc/dealloc).  In PAIR
+//               mode the leader CTA issues ONE tcgen05.mma.cta_group::2 (M = 256) per K-step for both CTAs.
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b, one accumulator row per thread; fused math; 128B-swizzled smem staging
+//               tile; one TMA bulk store / reduce-add per 128-byte-wide column chunk)
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of
-// tile i+1.  Tile = 128 x BN x 64 with BN in {128, 256}.  Operands may be K-major or MN-major (UMMA descriptor +
+// tile i+1.  Tile = 128 x BN x 64 per CTA with BN in {128, 256}.  Operands may be K-major or MN-major (UMMA descriptor +
 // instruction-descriptor major bits), which is what lets dgrad and wgrad read activations/weights in place.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -660,7 +661,7 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
     splits = 1;
   } else if (splits <= 0) {
     // Pick the split count that fills whole waves of the persistent grid: efficiency = items / (waves * SMs), with a
-    // small penalty per split (each split adds one fp32 red.add pass over the output tile).
+    // small penalty per split (each split adds one fp32 reduce-add pass over the output tile).
     const int tiles = ((p.num_m + cl - 1) / cl) * p.num_n * cl;
     const int max_splits = p.kblocks / 8 > 0 ? (p.kblocks / 8 < 32 ? p.kblocks / 8 : 32) : 1;  // >= 8 k-blocks each
     double best = -1.0;
