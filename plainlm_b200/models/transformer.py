@@ -126,31 +126,34 @@ class Transformer(nn.Module):
       h = layer(h, table, seg)
     return PF.linear(self.out_norm(h), self.lm_head.weight)
 
+  # Initialisation draws from the global torch RNG in exactly the reference's order (transformer.py:102-103,116-129):
+  # first every Linear / Embedding weight in module-traversal order at std 0.02, then the two residual-branch output
+  # projections of each block again at 0.02 / sqrt(2 L) — so a given seed yields the reference's weights bit for bit.
+  BASE_STD = 0.02
+
   def _init_weights(self, module):
-    if isinstance(module, nn.Linear):
-      torch.nn.init.normal_(module.weight, mean=0.0, std=0.02)
-      if module.bias is not None:
-        torch.nn.init.zeros_(module.bias)
-    elif isinstance(module, nn.Embedding):
-      torch.nn.init.normal_(module.weight, mean=0.0, std=0.02)
+    if isinstance(module, (nn.Linear, nn.Embedding)):
+      module.weight.data.normal_(mean=0.0, std=self.BASE_STD)
+      bias = getattr(module, 'bias', None)
+      if bias is not None:
+        bias.data.zero_()
 
   def _scale_residual_branches(self):
-    for n, p in self.named_parameters():
-      if n.endswith('fc2.weight'):
-        torch.nn.init.normal_(p, mean=0.0, std=0.02 / math.sqrt(2 * self.n_layers))
-      if n.endswith('w_out.weight'):
-        torch.nn.init.normal_(p, mean=0.0, std=0.02 / math.sqrt(2 * self.n_layers))
+    branch_std = self.BASE_STD / math.sqrt(2 * self.n_layers)
+    for name, param in self.named_parameters():
+      for suffix in ('fc2.weight', 'w_out.weight'):
+        if name.endswith(suffix):
+          param.data.normal_(mean=0.0, std=branch_std)
 
   def tie_weights(self):
     self.lm_head.weight = self.embed_tokens.weight
 
   def count_params(self, non_embedding=True):
-    n_params = sum(p.numel() for p in self.parameters())
+    """Number of parameters; `non_embedding` leaves out the token embedding and an untied LM head (reference :134-140)."""
+    skip = set()
     if non_embedding:
-      n_params -= self.embed_tokens.weight.numel()
-      if self.lm_head.weight is not self.embed_tokens.weight:
-        n_params -= self.lm_head.weight.numel()
-    return n_params
+      skip = {id(self.embed_tokens.weight), id(self.lm_head.weight)}
+    return sum(p.numel() for p in self.parameters() if id(p) not in skip)
 
   # ---------------------------------------------------------------------------- B200 runtime
   def rope_table(self, device):

@@ -1,44 +1,52 @@
-"""Process-group bring-up and teardown (reference: torch_utils.py), one process per GPU under torchrun."""
+"""Process bring-up / teardown for one process per GPU under torchrun (reference: torch_utils.py).
+
+`pytorch_setup(cfg) -> (local_rank, world_size, device, master_process)` and `destroy_ddp()` keep the reference's
+contract.  Two deliberate differences: the CUDA device of the rank is actually made current (the reference constructs
+a `torch.cuda.device` context at :21 and never enters it), and a machine without a GPU raises — there is no CPU path.
+"""
 
 import os
 import random
 
 import numpy as np
 import torch
-from torch.distributed import destroy_process_group, init_process_group
+import torch.distributed as dist
+
+
+def _torchrun_env():
+  """(rank, local_rank, world_size) from the launcher's environment, or None for a single un-launched process."""
+  if 'RANK' not in os.environ or int(os.environ['RANK']) < 0:
+    return None
+  return tuple(int(os.environ[k]) for k in ('RANK', 'LOCAL_RANK', 'WORLD_SIZE'))
+
+
+def _seed_everything(seed):
+  for seeder in (random.seed, np.random.seed, torch.manual_seed):
+    seeder(seed)
 
 
 def pytorch_setup(cfg):
-  """reference: torch_utils.py:11-57 -> (local_rank, world_size, device, master_process).
-  Differences: the CUDA device is actually selected (the reference builds a `torch.cuda.device` context it never
-  enters, :21), and without a GPU this raises instead of falling back to the CPU."""
-  ddp = int(os.environ.get('RANK', -1)) != -1
   if not torch.cuda.is_available():
     raise RuntimeError('plainlm_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
-  if ddp:
-    rank = int(os.environ['RANK'])
-    local_rank = int(os.environ['LOCAL_RANK'])
-    world_size = int(os.environ['WORLD_SIZE'])
-    torch.cuda.set_device(local_rank)
-    init_process_group(backend='nccl', device_id=torch.device(f'cuda:{local_rank}'))
-    device = f'cuda:{local_rank}'
-    master_process = rank == 0
-    seed_offset = rank
+  env = _torchrun_env()
+  if env is None:
+    rank, local_rank, world_size, device = 0, None, 1, 'cuda'
   else:
-    master_process, seed_offset, local_rank, world_size, device = True, 0, None, 1, 'cuda'
-
-  random.seed(cfg.seed + seed_offset)
-  np.random.seed(cfg.seed + seed_offset)
-  torch.manual_seed(cfg.seed + seed_offset)
+    rank, local_rank, world_size = env
+    device = f'cuda:{local_rank}'
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group(backend='nccl', device_id=torch.device(device))
+  _seed_everything(cfg.seed + rank)  # ranks draw different streams; rank 0's weights are broadcast by the engine
 
   torch.backends.cuda.matmul.allow_tf32 = getattr(cfg, 'cuda_matmul_allow_tf32', False)
   torch.backends.cudnn.allow_tf32 = getattr(cfg, 'cudnn_allow_tf32', True)
-  if hasattr(cfg, 'set_memory_fraction'):
-    torch.cuda.set_per_process_memory_fraction(cfg.set_memory_fraction, device=device)
-  return local_rank, world_size, device, master_process
+  fraction = getattr(cfg, 'set_memory_fraction', None)
+  if fraction is not None:
+    torch.cuda.set_per_process_memory_fraction(fraction, device=device)
+  return local_rank, world_size, device, rank == 0
 
 
 def destroy_ddp():
-  if torch.distributed.is_initialized():
-    torch.distributed.barrier()
-    destroy_process_group()
+  if dist.is_initialized():
+    dist.barrier()
+    dist.destroy_process_group()
