@@ -1,4 +1,7 @@
-"""`from optim import intialize_optimizer, initialize_scheduler` (reference engine.py:9) -> the B200 implementation."""
-from plainlm_b200.optim import intialize_optimizer, initialize_scheduler  # noqa: F401
+"""Shim: the reference's `engine/engine.py:9` does `from optim import intialize_optimizer, initialize_scheduler`; with
+`dropin/` ahead of the reference on PYTHONPATH those two names resolve to the B200 implementation."""
+import plainlm_b200.optim as _impl
 
-__all__ = ['intialize_optimizer', 'initialize_scheduler']
+intialize_optimizer = _impl.intialize_optimizer  # (sic) the reference's spelling
+initialize_scheduler = _impl.initialize_scheduler
+__all__ = ('initialize_scheduler', 'intialize_optimizer')
