@@ -643,7 +643,8 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   {
     const double a_bytes = 2.0 * static_cast<double>(a->M) * static_cast<double>(a->K);
     const double b_bytes = 2.0 * static_cast<double>(a->N) * static_cast<double>(a->K);
-    p.n_fastest = (a_bytes > 48e6 && b_bytes < a_bytes) ? 1 : 0;
+    p.n_fastest = (b_bytes < a_bytes) ? 1 : 0;  // measured with CTA pairs: walking N wins whenever the weights are the
+                                                // smaller operand (fc1 151 -> 147 us, out-proj 55 -> 52 us), even if A fits in L2
     const int forced = env_int("PLM_GEMM_RASTER", -1);
     if (forced == 0 || forced == 1) p.n_fastest = forced;
   }
