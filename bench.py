@@ -10,8 +10,10 @@ Weak scaling: per-GPU work is fixed, `value` is the whole-job tokens/s.  Two tim
   value : micro-batches already resident in HBM when the clock starts
   e2e   : TorchEngine.step(batch) with HOST (pinned) batches — H2D of ids every micro-step and a D2H read of the loss
           every optimizer step inside the timed region
-Rank 0 prints ONE JSON line.  `--impl reference` times the reference's CPU path (the oracle restatement — the
-reference is pure Python/PyTorch) on the host cores for the same config and metric.
+Rank 0 prints ONE JSON line.  `--impl reference` times the reference's own CPU path — the UNMODIFIED reference installed
+into baseline/_ref by baseline/install_ref.sh (git-ignored, travels with the gpurun snapshot) — on the host cores for the
+same config and metric; the bench line of our arm also carries `gpu_eager_reference`: that same reference run eagerly
+on the same B200 (torch library kernels), in its own process before our engine allocates anything.
 """
 
 import argparse
@@ -48,11 +50,31 @@ def glu_hidden(d):
   return 256 * ((int(8 / 3 * d) + 255) // 256)
 
 
-def flops_per_token(c):
-  """F_tok = 6 N_mm + 6 L d T (causal attention, flash recompute not counted)."""
+def flops_per_token(c, pairs_per_token=None):
+  """F_tok = 6 N_mm + 6 L d T for causal attention (flash recompute not counted).  Document-masked:
+  the attention term becomes 12 L d x (allowed (query, key) pairs per token) = 12 L d sum_docs len (len + 1) / 2 / tokens;
+  full causal has (T + 1) / 2 ~ T / 2 pairs per token, which gives the 6 L d T above."""
   d, L, T, V = c['d_model'], c['n_layers'], c['seq_len'], c['vocab_size']
   n_mm = L * (4 * d * d + 3 * d * glu_hidden(d)) + d * V
-  return 6 * n_mm + 6 * L * d * T
+  if pairs_per_token is None:
+    return 6 * n_mm + 6 * L * d * T
+  return 6 * n_mm + 12 * L * d * pairs_per_token
+
+
+def doc_pairs_per_token(docs, T):
+  """Allowed (query, key) pairs per token under intra-document causal masking: positions 0..T-1 of a row whose
+  documents have the given lengths (summing to T + 1; the last position is only ever a target)."""
+  pairs = tokens = 0
+  for lengths in docs:
+    left = T
+    for n in lengths:
+      n = min(n, left)
+      pairs += n * (n + 1) // 2
+      left -= n
+      if left <= 0:
+        break
+    tokens += T
+  return pairs / tokens
 
 
 def make_cfgs(c, steps_budget):
@@ -143,17 +165,20 @@ def load_peaks():
   return {'hbm_gbs': 6650.0, 'tf_burst': 1590.0, 'tf_sustained': 1400.0, 'source': 'fallback'}
 
 
-def op_work(name, tag, c):
+def op_work(name, tag, c, pairs_per_token=None):
   """Algorithmic work of one op call: ('tensor', flops) or ('hbm', bytes) — DESIGN.md §kernels."""
   if name == 'gemm':
     M, N, K = tag[0], tag[1], tag[2]
     return 'tensor', 2.0 * M * N * K
   if name in ('attn_fwd', 'attn_bwd'):
     B, T, H, hd = tag[:4]
-    fwd = 4.0 * B * H * hd * T * (T + 1) / 2  # causal pairs x (QK^T + PV) x 2 flop
+    pairs = (T + 1) / 2 if (pairs_per_token is None or not tag[4]) else pairs_per_token
+    fwd = 4.0 * B * H * hd * T * pairs  # allowed pairs x (QK^T + PV) x 2 flop
     return 'tensor', fwd if name == 'attn_fwd' else 2.0 * fwd
   n = tag[0] if tag else 0
-  per_elt = {'rmsnorm_fwd': 6, 'rmsnorm_bwd': 16, 'swiglu_fwd': 3, 'swiglu_bwd': 5, 'embed_fwd': 8, 'embed_bwd': 12,
+  # bytes per element of the op's FIRST tensor argument: swiglu_fwd's is u [M, 2F] (2 B read + 1 B written per u
+  # element = 6 B per hidden element); swiglu_bwd's is dh [M, F] (dh 2 + u 4 + du 4 = 10 B per hidden element)
+  per_elt = {'rmsnorm_fwd': 6, 'rmsnorm_bwd': 16, 'swiglu_fwd': 3, 'swiglu_bwd': 10, 'embed_fwd': 8, 'embed_bwd': 12,
              'ce_fwd_bwd': 6, 'sumsq': 4, 'adamw_step': 30, 'signsgd_step': 22, 'cast_f32_bf16': 6,
              'cast_bf16_f32': 6, 'colsum_accum': 4}.get(name, 4)
   return 'hbm', float(per_elt) * n
@@ -182,6 +207,12 @@ def run_ours(args):
 
   K, W = args.steps, max(args.warmup, 3)
   accum, B, T = c['grad_accumulation_steps'], c['micro_batch_size'], c['seq_len']
+  # The unmodified reference, eager, on this same GPU — in its own process, before this one allocates:
+  # torch's library kernels (cuBLASLt, SDPA, ATen, fused AdamW), same config, same synthetic tokens.  Reported beside
+  # our number; not part of any timed region.
+  gpu_ref = None
+  if rank == 0 and world == 1 and not args.no_gpu_reference:
+    gpu_ref = reference_subprocess(args.config, 'cuda', steps=3, warmup=2, optim=c['optim'])
   mcfg, tcfg, _ = make_cfgs(c, 2 * (K + W) + 4)
   torch.manual_seed(100 + rank)  # reference: torch_utils.py:35-37 (rank 0's weights are broadcast by the engine)
   model, _ = construct_model(mcfg) if rank == 0 or True else (None, None)
@@ -275,13 +306,14 @@ def run_ours(args):
   tokens_per_step = B * T * accum * world
   value = tokens_per_step * K / (ms_value / 1e3)
   e2e_value = tokens_per_step * K / (ms_e2e / 1e3)
-  ftok = flops_per_token(c)
+  ppt = doc_pairs_per_token(docs, T) if docs else None  # document masking: count only the allowed (query, key) pairs
+  ftok = flops_per_token(c, ppt)
   peaks = load_peaks()
 
   if rank == 0 and os.environ.get('PLM_BENCH_DETAIL'):  # per-(kernel, shape) table of the instrumented step
     rows = []
     for (name, tag), (cnt, ms) in sorted(summ.items(), key=lambda kv: -kv[1][1]):
-      kind, work = op_work(name, tag, c)
+      kind, work = op_work(name, tag, c, ppt)
       rate = work * cnt / (ms / 1e3) / (1e12 if kind == 'tensor' else 1e9)
       rows.append(f'{name:22s} {str(tag):44s} calls {cnt:4d}  total {ms:8.3f} ms  avg {ms / cnt * 1e3:8.1f} us  '
                   f'{rate:8.1f} {"TF/s" if kind == "tensor" else "GB/s"}')
@@ -300,7 +332,7 @@ def run_ours(args):
     total_ms = sum(v[1] for v in summ.values())
     by_kernel = {}
     for (name, tag), (cnt, ms) in summ.items():
-      kind, work = op_work(name, tag, c)
+      kind, work = op_work(name, tag, c, ppt)
       rec = by_kernel.setdefault(name, {'ms': 0.0, 'work': 0.0, 'calls': 0, 'kind': kind})
       rec['ms'] += ms
       rec['work'] += work * cnt
@@ -328,7 +360,7 @@ def run_ours(args):
                 'by_kernel_frac': {k: round((v['work'] / (v['ms'] / 1e3) / (1e12 if v['kind'] == 'tensor' else 1e9)) /
                                             (peaks['tf_sustained'] if v['kind'] == 'tensor' else peaks['hbm_gbs']), 3)
                                    for k, v in by_kernel.items() if v['ms'] > 0}}
-    cpu = cpu_baseline(c, steps=1, warmup=0) if (world == 1 and not args.no_cpu_baseline) else None
+    cpu = cpu_baseline(args.config, c, steps=3, warmup=1) if (world == 1 and not args.no_cpu_baseline) else None
     out = {
       'metric': 'tokens/sec (420M GLU/RoPE LM train step)' if args.config == '420m' else f'tokens/sec ({args.config} train step)',
       'value': round(value, 1), 'unit': 'tokens/s', 'n_gpus': world, 'steps': K, 'warmup': W,
@@ -339,7 +371,8 @@ def run_ours(args):
                              f'{"document-masked" if c["intra_doc_masking"] else "causal"} attention',
                  'global_batch_tokens': tokens_per_step, 'seq_len': T, 'parallelism': f'dp{world}',
                  'l2': 'working set (>=14 GB of activations + 5 GB of optimizer state per step) >> 126 MB L2: no flush needed'},
-      'mfu': {'flops_per_token': ftok, 'model_tflops': round(value * ftok / world / 1e12, 1),
+      'mfu': {'flops_per_token': int(ftok), 'attention_pairs_per_token': round(ppt if ppt is not None else (T + 1) / 2, 1),
+              'model_tflops': round(value * ftok / world / 1e12, 1),
               'vs_nominal_2250': round(value * ftok / world / 2250e12, 4),
               'vs_measured_sustained': round(value * ftok / world / (peaks['tf_sustained'] * 1e12), 4)},
       'e2e': {'value': round(e2e_value, 1), 'unit': 'tokens/s', 'ms_per_step': round(ms_e2e / K, 3),
@@ -352,20 +385,51 @@ def run_ours(args):
     }
     if cpu is not None:
       out['cpu_baseline'] = cpu
+    if gpu_ref is not None:
+      out['gpu_eager_reference'] = gpu_ref
     print(json.dumps(out))
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
 
 
-def cpu_baseline(c, steps, warmup):
-  """The reference's CPU path (fp32, engine.py:73-75) restated by the oracle, timed on this box's host cores on a
-  bounded sample: `steps` micro-batches of ONE sequence (fwd + bwd + clip + AdamW each)."""
+def reference_subprocess(config, device, steps, warmup, optim='adamw', timeout=1500):
+  """Runs baseline/run_reference.py (the unmodified reference from baseline/_ref) in its own process; returns its JSON
+  dict, or {'unavailable': why}."""
+  script = os.path.join(ROOT, 'baseline', 'run_reference.py')
+  cmd = [sys.executable, script, '--device', device, '--config', config, '--steps', str(steps), '--warmup', str(warmup),
+         '--optim', optim]
+  env = dict(os.environ, TORCHDYNAMO_DISABLE='1')
+  for k in ('OMP_NUM_THREADS', 'MKL_NUM_THREADS', 'RANK', 'LOCAL_RANK', 'WORLD_SIZE', 'MASTER_ADDR', 'MASTER_PORT'):
+    env.pop(k, None)  # torchrun pins OMP_NUM_THREADS=1 for its children; the reference process is single, un-distributed
+  try:
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+  except subprocess.TimeoutExpired:
+    return {'unavailable': f'reference run exceeded {timeout} s'}
+  for line in reversed(p.stdout.splitlines()):
+    if line.startswith('{'):
+      return json.loads(line)
+  return {'unavailable': f'reference run failed (rc {p.returncode}): {p.stderr.strip()[-300:]}'}
+
+
+def cpu_baseline(config, c, steps, warmup):
+  """The reference's CPU path timed on this box's host cores on a bounded sample: `steps` micro-batches of ONE sequence
+  (fwd + bwd + clip + AdamW each) after `warmup` untimed ones.  kind "reference": the unmodified reference from
+  baseline/_ref (construct_model + TorchEngine.step, fp32 as engine.py:73-75 dictates for the CPU); kind "port": the
+  oracle restatement, only when baseline/_ref is not on the box."""
+  T = c['seq_len']
+  res = reference_subprocess(config, 'cpu', steps, warmup, optim=c['optim'])
+  if 'unavailable' not in res:
+    return {'value': res['value'], 'unit': 'tokens/s', 'cores': res['threads'], 'host_cpus': res['host_cpus'],
+            'kind': 'reference',
+            'sample': f"{res['steps']} micro-batch(es) of 1 x {T} tokens after {res['warmup']} warm-up, fp32, "
+                      f"fwd+bwd+clip+AdamW through the reference's TorchEngine.step, {res['seconds']:.1f} s",
+            'ms_per_step': res['ms_per_step'], 'loss': res['loss']}
   import torch
 
   from oracle import plainlm_oracle as orc
 
-  T = c['seq_len']
+  torch.set_num_threads(os.cpu_count() or 1)
   _, _, tdict = make_cfgs(c, 10)
   cfg = dict(tdict, grad_accumulation_steps=1, n_heads=c['n_heads'], dtype='float32', intra_doc_masking=False)
   params = orc.init_params(c['vocab_size'], c['d_model'], c['n_layers'], c['n_heads'], seed=100)
@@ -380,19 +444,20 @@ def cpu_baseline(c, steps, warmup):
       times.append(dt)
   tot = sum(times)
   return {'value': round(T * len(times) / tot, 1), 'unit': 'tokens/s', 'cores': torch.get_num_threads(),
-          'host_cpus': os.cpu_count(), 'kind': 'port',
-          'sample': f'{len(times)} micro-batch(es) of 1 x {T} tokens, fp32, fwd+bwd+clip+AdamW, {tot:.1f} s',
+          'host_cpus': os.cpu_count(), 'kind': 'port', 'why_port': res['unavailable'],
+          'sample': f'{len(times)} micro-batch(es) of 1 x {T} tokens after {warmup} warm-up, fp32, fwd+bwd+clip+AdamW, {tot:.1f} s',
           'ms_per_step': round(1e3 * tot / len(times), 1), 'loss': round(loss, 4)}
 
 
 def run_reference(args):
-  """--impl reference: the reference's own CPU implementation of the path (oracle port, all host threads)."""
+  """--impl reference: the reference's own CPU implementation of the path — the unmodified reference from baseline/_ref
+  (the oracle port only if that is missing) — on all host threads.  Under torchrun only rank 0 works."""
   rank = int(os.environ.get('RANK', 0))
   if rank != 0:
     return
   c = CONFIGS[args.config]
   K, W = args.steps, args.warmup
-  res = cpu_baseline(c, steps=K, warmup=W)
+  res = cpu_baseline(args.config, c, steps=K, warmup=W)
   T = c['seq_len']
   out = {
     'impl': 'reference',
@@ -418,6 +483,7 @@ def main():
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--config', default='420m', choices=sorted(CONFIGS))
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-gpu-reference', action='store_true')
   args = ap.parse_args()
   if args.impl == 'reference':
     args.steps = 3 if args.steps is None else args.steps

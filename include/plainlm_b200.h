@@ -97,10 +97,17 @@ int plm_gemm_bf16(const plm_gemm_args* args, plm_stream_t stream);
  *      data/datasets/data_prep_utils.py:7-23 + engine/engine.py:19-23 (block-diagonal causal mask).
  * out: bf16 [B*T, H*hd] (already in the [B,T,H*hd] layout w_out consumes: no transpose/contiguous copy).
  * lse: fp32 [B, H, T] natural-log logsumexp of the scaled scores.
- * Supported: hd == 64, T % 128 == 0.
+ * Supported: hd == 64; any T >= 1 (ragged last tile).
  */
 int plm_attn_fwd(const void* qkv, const int32_t* seg_start, void* out, float* lse, int32_t B, int32_t T, int32_t H,
                  int32_t hd, plm_stream_t stream);
+/* Diagnostics / A-B measurement only (tools/gpu_kernel_check.py): the same forward with an explicit kernel variant
+ * (number of score pairs out of every 4 whose exp2 runs as an FMA-pipe polynomial instead of MUFU.EX2: 0..2; < 0 = the
+ * default plm_attn_fwd uses), and the round-1 kernel (one query tile per CTA) kept as the baseline to beat. */
+int plm_attn_fwd_variant(const void* qkv, const int32_t* seg_start, void* out, float* lse, int32_t B, int32_t T,
+                         int32_t H, int32_t hd, int32_t variant, plm_stream_t stream);
+int plm_attn_fwd_v1(const void* qkv, const int32_t* seg_start, void* out, float* lse, int32_t B, int32_t T, int32_t H,
+                    int32_t hd, plm_stream_t stream);
 
 /* Backward.  dout: bf16 [B*T, H*hd].  dqkv: bf16 [B*T, 3*H*hd] (fully overwritten); dq and dk are rotated back by the
  * inverse RoPE (transpose of models/embeddings.py:15-30) so dqkv is the gradient of the QKV GEMM's un-rotated output.

@@ -38,6 +38,8 @@ SIGNATURES = {
   'plm_device_check': (c_int32, []),
   'plm_gemm_bf16': (c_int32, [ctypes.POINTER(GemmArgs), _P]),
   'plm_attn_fwd': (c_int32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+  'plm_attn_fwd_variant': (c_int32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
+  'plm_attn_fwd_v1': (c_int32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
   'plm_attn_bwd': (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
   'plm_rope_qk': (c_int32, [_P, _P, _I64, _I32, _I32, _I32, _I32, _P]),
   'plm_rmsnorm_fwd': (c_int32, [_P, _P, _P, _P, _I64, _I32, _F, _P]),

@@ -70,10 +70,17 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_BF16, res
 
 
 # ---------------------------------------------------------------------------------------------- attention
-def attn_fwd(qkv, out, lse, B, T, H, hd, seg_start=None):
+def attn_fwd(qkv, out, lse, B, T, H, hd, seg_start=None, variant=None):
+  """variant (diagnostics): None = the library's default kernel; 0..2 = plm_attn_fwd_variant; 'v1' = the round-1 kernel."""
   lib = _lib.load()
-  check(lib.plm_attn_fwd(_ptr(qkv, bf16, 'qkv'), _ptr(seg_start, torch.int32, 'seg_start'), _ptr(out, bf16, 'out'),
-                         _ptr(lse, f32, 'lse'), B, T, H, hd, _stream()), 'plm_attn_fwd')
+  args = (_ptr(qkv, bf16, 'qkv'), _ptr(seg_start, torch.int32, 'seg_start'), _ptr(out, bf16, 'out'),
+          _ptr(lse, f32, 'lse'), B, T, H, hd)
+  if variant is None:
+    check(lib.plm_attn_fwd(*args, _stream()), 'plm_attn_fwd')
+  elif variant == 'v1':
+    check(lib.plm_attn_fwd_v1(*args, _stream()), 'plm_attn_fwd_v1')
+  else:
+    check(lib.plm_attn_fwd_variant(*args, int(variant), _stream()), 'plm_attn_fwd_variant')
   return out, lse
 
 

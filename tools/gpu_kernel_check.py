@@ -158,20 +158,20 @@ def _make_seg(B, T, seed=0):
   return seg.reshape(-1)
 
 
-def case_attn_fwd(B, T, H, doc=False):
+def case_attn_fwd(B, T, H, doc=False, variant=None, scale=1.0):
   import torch
   from plainlm_b200 import ops
 
   hd, dev = 64, 'cuda'
   torch.manual_seed(1)
-  qkv = torch.randn(B * T, 3 * H * hd, device=dev).to(torch.bfloat16)
+  qkv = (torch.randn(B * T, 3 * H * hd, device=dev) * scale).to(torch.bfloat16)
   seg = _make_seg(B, T).to(dev) if doc else None
   out = torch.full((B * T, H * hd), float('nan'), device=dev, dtype=torch.bfloat16)
   lse = torch.full((B, H, T), float('nan'), device=dev)
-  ops.attn_fwd(qkv, out, lse, B, T, H, hd, seg_start=seg)
+  ops.attn_fwd(qkv, out, lse, B, T, H, hd, seg_start=seg, variant=variant)
   torch.cuda.synchronize()
   o_ref, lse_ref = _attn_ref(qkv, B, T, H, hd, seg)
-  r = _err(f'attn_fwd B{B} T{T} H{H} doc{int(doc)} out', out, o_ref)
+  r = _err(f'attn_fwd B{B} T{T} H{H} doc{int(doc)} variant {variant} scale {scale} out', out, o_ref)
   r2 = _err('lse', lse, lse_ref)
   r['lse_max_abs'] = r2['max_abs']
   r['lse_nan'] = r2['nan']
@@ -651,42 +651,6 @@ def case_attn_bwd_trace():
   return [{'case': 'timeline', 'events': [f'{t:7d} {n}' for t, n in ev]}]
 
 
-def case_attn_fwd_trace():
-  """clock64 timeline of one attention-forward CTA (PLM_ATTN_FWD_TRACE)."""
-  import torch
-  from plainlm_b200 import ops
-
-  dev = 'cuda'
-  B, T, H, hd = 8, 2048, 16, 64
-  d = H * hd
-  qkv = torch.randn(B * T, 3 * d, device=dev).to(torch.bfloat16)
-  out = torch.empty(B * T, d, device=dev, dtype=torch.bfloat16)
-  lse = torch.empty(B, H, T, device=dev)
-  for _ in range(2):
-    ops.attn_fwd(qkv, out, lse, B, T, H, hd)
-  buf = torch.zeros(128, device=dev, dtype=torch.int64)
-  os.environ['PLM_ATTN_FWD_TRACE'] = hex(buf.data_ptr())
-  ops.attn_fwd(qkv, out, lse, B, T, H, hd)
-  os.environ.pop('PLM_ATTN_FWD_TRACE')
-  torch.cuda.synchronize()
-  v = buf.cpu().tolist()
-  t0 = v[0]
-  ev = []
-  lab_s = ['top', 's_full', 'S in registers', 'max done', 'exp pass done', 'pv_done / rescale / P stored', 'p_full sent', '-']
-  lab_c = ['s_empty seen', 'S(it+1) issued', 'p_full seen', 'PV issued']
-  for itr in range(4):
-    for k in range(8):
-      if v[itr * 8 + k]:
-        ev.append((v[itr * 8 + k] - t0, f'SM it{6 + itr} {lab_s[k]}'))
-    for k in range(4):
-      if v[64 + itr * 4 + k]:
-        ev.append((v[64 + itr * 4 + k] - t0, f'CT it{6 + itr} {lab_c[k]}'))
-  ev.sort()
-  cyc, ns = v[121] - v[120], v[123] - v[122]
-  summary = f'CTA (16 key tiles): {cyc} cycles in {ns} ns = {cyc / max(ns, 1):.3f} GHz; step 6 starts {t0 - v[120]} cycles in'
-  return [{'case': 'timeline', 'summary': summary, 'events': [f'{t:7d} {n}' for t, n in ev]}]
-
-
 def case_attn_perf():
   import torch
   from plainlm_b200 import ops
@@ -705,6 +669,10 @@ def case_attn_perf():
   res = []
   for label, fn, fl in (
     ('attn_fwd', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd), flops_fwd),
+    ('attn_fwd v1 (round 1)', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant='v1'), flops_fwd),
+    ('attn_fwd variant 0', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant=0), flops_fwd),
+    ('attn_fwd variant 1', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant=1), flops_fwd),
+    ('attn_fwd variant 2', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant=2), flops_fwd),
     ('attn_bwd', lambda: ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd), 2.5 * flops_fwd),
   ):
     for _ in range(3):
@@ -751,8 +719,18 @@ CASES['gemm_wgrad_atomic_split'] = lambda: case_gemm(1024, 512, 4096, False, Fal
 CASES['gemm_wgrad_atomic_1'] = lambda: case_gemm(512, 512, 1024, False, False, 'atomic', 0, 1)
 CASES['attn_fwd_1tile'] = lambda: case_attn_fwd(1, 128, 1)
 CASES['attn_fwd_2tile'] = lambda: case_attn_fwd(1, 256, 1)
+CASES['attn_fwd_3tile'] = lambda: case_attn_fwd(1, 384, 2)      # odd number of query tiles: the last pair is half empty
+CASES['attn_fwd_ragged'] = lambda: case_attn_fwd(2, 200, 2)     # T not a multiple of 64
 CASES['attn_fwd_multi'] = lambda: case_attn_fwd(2, 512, 3)
+CASES['attn_fwd_multi_v1'] = lambda: case_attn_fwd(2, 512, 3, variant=1)
+CASES['attn_fwd_multi_v2'] = lambda: case_attn_fwd(2, 512, 3, variant=2)
+CASES['attn_fwd_multi_old'] = lambda: case_attn_fwd(2, 512, 3, variant='v1')
+CASES['attn_fwd_peaky'] = lambda: case_attn_fwd(2, 512, 2, scale=4.0)   # large logits: exercises the lazy O rescale
+CASES['attn_fwd_peaky_v2'] = lambda: case_attn_fwd(2, 512, 2, scale=4.0, variant=2)
 CASES['attn_fwd_doc'] = lambda: case_attn_fwd(2, 512, 2, doc=True)
+CASES['attn_fwd_doc_v2'] = lambda: case_attn_fwd(2, 512, 2, doc=True, variant=2)
+CASES['attn_fwd_many_items'] = lambda: case_attn_fwd(3, 1024, 40)  # 480 items: several rounds of the persistent schedule
+CASES['attn_fwd_long'] = lambda: case_attn_fwd(1, 4096, 2)
 CASES['attn_bwd_1tile'] = lambda: case_attn_bwd(1, 128, 1)
 CASES['attn_bwd_2tile'] = lambda: case_attn_bwd(1, 256, 1)
 CASES['attn_bwd_multi'] = lambda: case_attn_bwd(2, 512, 3)
@@ -765,7 +743,6 @@ CASES['gemm_epi_perf'] = case_gemm_epi_perf
 CASES['gemm_feed_probe'] = case_gemm_feed_probe
 CASES['gemm_n1024_probe'] = case_gemm_n1024_probe
 CASES['attn_bwd_trace'] = case_attn_bwd_trace
-CASES['attn_fwd_trace'] = case_attn_fwd_trace
 CASES['gemm_sustained'] = case_gemm_sustained
 
 
