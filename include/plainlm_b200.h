@@ -28,7 +28,7 @@ extern "C" {
 #define PLM_ERR_CUDA (-2)        /* CUDA runtime / driver error while encoding a descriptor or launching */
 #define PLM_ERR_UNSUPPORTED (-3) /* shape outside what the sm_100a kernels implement                     */
 
-#define PLM_ABI_VERSION 2
+#define PLM_ABI_VERSION 3
 
 typedef void* plm_stream_t;
 
@@ -87,6 +87,11 @@ typedef struct plm_gemm_args {
 } plm_gemm_args;
 
 int plm_gemm_bf16(const plm_gemm_args* args, plm_stream_t stream);
+/* Diagnostics / A-B measurement only: process-global overrides of the automatic tile choices of plm_gemm_bf16
+ * (bn: 0 auto | 128 | 256; raster: -1 auto | 0 walk M | 1 walk N; cluster: 0 auto | 1 | 2; pair: 1 = CTA-pair MMA when
+ * clustered, 0 = two cta_group::1 MMAs; debug: timing-experiment mask, only honoured by -DPLM_GEMM_DEBUG builds).
+ * plm_gemm_set_tuning(0, -1, 0, 1, 0) restores the defaults.  Nothing on the launch path reads the environment. */
+int plm_gemm_set_tuning(int32_t bn, int32_t raster, int32_t cluster, int32_t pair, int32_t debug);
 
 /* ------------------------------------------------------------------------------------------------ attention
  * Causal / document-masked flash attention (models/transformer.py:53-63, F.scaled_dot_product_attention) on tcgen05.
@@ -219,10 +224,6 @@ int plm_cast_bf16_f32(const void* src, float* dst, int64_t n, float scale, plm_s
  * data/datasets/data_prep_utils.py:7-23 cropped to [:T,:T] (engine/engine.py:23). */
 int plm_seg_start_from_lengths(const int32_t* lengths, const int32_t* offsets, int32_t* seg_start, int32_t B,
                                int32_t T, plm_stream_t stream);
-
-/* Diagnostics: clock64() stamps of the attention-backward kernel's phase boundaries (HOST pointer, n <= 256), written
- * by one CTA when the environment variable PLM_ATTN_TRACE is set; all zeros otherwise.  Synchronises the device. */
-int plm_debug_counters(unsigned long long* out, int32_t n, int32_t reset);
 
 #ifdef __cplusplus
 }

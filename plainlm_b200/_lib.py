@@ -37,6 +37,7 @@ SIGNATURES = {
   'plm_last_error': (ctypes.c_char_p, []),
   'plm_device_check': (c_int32, []),
   'plm_gemm_bf16': (c_int32, [ctypes.POINTER(GemmArgs), _P]),
+  'plm_gemm_set_tuning': (c_int32, [_I32, _I32, _I32, _I32, _I32]),
   'plm_attn_fwd': (c_int32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
   'plm_attn_fwd_variant': (c_int32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
   'plm_attn_fwd_v1': (c_int32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
@@ -62,7 +63,6 @@ SIGNATURES = {
   'plm_cast_f32_bf16': (c_int32, [_P, _P, _I64, _F, _P]),
   'plm_cast_bf16_f32': (c_int32, [_P, _P, _I64, _F, _P]),
   'plm_seg_start_from_lengths': (c_int32, [_P, _P, _P, _I32, _I32, _P]),
-  'plm_debug_counters': (c_int32, [ctypes.POINTER(ctypes.c_ulonglong), _I32, _I32]),
 }  # fmt: skip
 
 _lib = None
@@ -95,10 +95,15 @@ def load():
     fn = getattr(lib, name)  # AttributeError if the symbol is missing
     fn.restype = restype
     fn.argtypes = argtypes
-  if lib.plm_abi_version() != 2:
+  if lib.plm_abi_version() != 3:
     raise RuntimeError('libplainlm_b200.so ABI version mismatch')
   _lib = lib
   return lib
+
+
+def gemm_tuning(bn=0, raster=-1, cluster=0, pair=1, debug=0):
+  """Diagnostics: process-global overrides of plm_gemm_bf16's automatic tile choices (no arguments = defaults)."""
+  check(load().plm_gemm_set_tuning(bn, raster, cluster, pair, debug), 'plm_gemm_set_tuning')
 
 
 class PlmError(RuntimeError):

@@ -15,12 +15,14 @@
 // K are consumed as MN-major B operands straight from their TMA boxes — no transposes anywhere.  S^T / dP^T of step
 // i+1 are issued as soon as the compute warps have READ step i's tiles out of tensor memory, so the tensor pipe works
 // on the neighbouring step while the exp / dS math runs.  dK and dQ are rotated back through RoPE in the epilogues.
-// Measured (PLM_ATTN_TRACE timeline, tools/gpu_kernel_check.py --case attn_bwd_trace): a step takes ~3000 cycles, of
-// which ~1500 are the exp/dS math (MUFU-bound: 16384 ex2 per step at 16/clk/SM = 1024) and the rest hand-off latency.
+// Round 1 measured ~3000 cycles per step.  Its ncu source page (profiles/r2_attn_bwd_instruction_mix.md) showed the
+// kernel ISSUE-bound: 10.2 k warp-instructions per step = 2560 issue cycles per scheduler, of which only 2.1 k were the
+// exp / dS math: 36 % were mbarrier polling loops of waiting warps, the rest clock64 trace hooks and per-step address
+// arithmetic.  This version sleeps in hardware while waiting (ptx.cuh: mbar_try_wait), has no trace hooks and keeps
+// its loop-invariant addresses in registers.
 #include "common.cuh"
 #include "ptx.cuh"
 
-#include <cstdlib>
 #include <mutex>
 
 namespace plm {
@@ -48,15 +50,6 @@ __device__ __forceinline__ float ex2b(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-
-// Diagnostic counters exported through plm_debug_counters (unused in release builds: always zero).
-__device__ unsigned long long g_dbg_counters[256];
-
-// PLM_ATTN_TRACE=1: one CTA stamps clock64() at its phase boundaries for four steady-state steps.
-#define AB_TR(slot_)                                                                 \
-  do {                                                                               \
-    if (tr_on && it >= 6 && it < 10 && lane == 0) g_dbg_counters[(slot_)] = clock64(); \
-  } while (0)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -168,9 +161,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                 const __grid_constant__ CUtensorMap tmDQ,
                 const float* __restrict__ lse, const float* __restrict__ delta, const int32_t* __restrict__ seg_start,
                 const float* __restrict__ rope, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_acc, int T,
-                int H, float scale, float scale_log2, int trace) {
+                int H, float scale, float scale_log2) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const bool tr_on = trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == gridDim.z / 2;
   uint8_t* sK = smem;
   uint8_t* sV = smem + AB_TILE;
   uint8_t* sQ = smem + 2 * AB_TILE;                    // [AB_STAGES]
@@ -193,7 +185,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                                      // dS^T buffer may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
 
-  if ((smem_u32(smem) & 1023u) != 0) return;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128-byte-swizzle layout contract violated: fail the launch loudly
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -298,9 +290,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         if (it < n_it) {  // S^T / dP^T of step `it`
           const uint64_t q_desc = q_desc0 + st * (AB_TILE >> 4), do_desc = do_desc0 + st * (AB_TILE >> 4);
           mbar_wait(&qdo_full[st], (it / AB_STAGES) & 1);
-          AB_TR(64 + (it - 6) * 4 + 0);
           if (it > 0) mbar_wait(sdp_free, (it - 1) & 1);
-          AB_TR(64 + (it - 6) * 4 + 1);
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < AB_HD / 16; ++k) {
@@ -308,7 +298,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             umma_ss(tDP, v_desc + k * 2, do_desc + k * 2, idesc_s, k > 0 ? 1u : 0u);
           }
           umma_commit(s_full);
-          AB_TR(64 + (it - 6) * 4 + 2);
           if (++st == AB_STAGES) st = 0;
         }
         if (it > 0) {  // dQ of step it-1
@@ -321,7 +310,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
             umma_ss(tDQ, ds_desc_mn + k * (2048 >> 4), k_desc_mn + k * (2048 >> 4), idesc_nn, k > 0 ? 1u : 0u);
           umma_commit(dq_full);
           umma_commit(mma_done);
-          AB_TR(64 + (it - 6) * 4 + 3);
         }
       }
     }
@@ -335,14 +323,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       for (int it = 0; it < n_it; ++it) {
         const uint64_t do_desc = do_desc0 + st * (AB_TILE >> 4);
         mbar_wait(pds_ready, it & 1);
-        AB_TR(96 + (it - 6) * 4 + 0);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < AB_T / 16; ++k)
           umma_ts(tDV, tP + k * 8, do_desc + k * (2048 >> 4), idesc_kn, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(mma_done);
         umma_commit(&qdo_empty[st]);
-        AB_TR(96 + (it - 6) * 4 + 1);
         if (++st == AB_STAGES) st = 0;
       }
     }
@@ -357,7 +343,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       for (int it = 0; it < n_it; ++it) {
         const uint64_t q_desc = q_desc0 + st * (AB_TILE >> 4);
         mbar_wait(pds_ready, it & 1);
-        AB_TR(128 + (it - 6) * 4 + 0);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < AB_T / 16; ++k)
@@ -365,7 +350,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
                   (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(mma_done);
         umma_commit(&qdo_empty[st]);
-        AB_TR(128 + (it - 6) * 4 + 1);
         if (++st == AB_STAGES) st = 0;
       }
     }
@@ -416,18 +400,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     int st = 0;
     for (int it = 0; it < n_it; ++it) {
       const int i = j + it;
-      const bool trw = tr_on && (warp == 0 || warp == 15);
-      const int trb = (warp == 0 ? 0 : 160) + (it - 6) * 8;
-#define AB_TRC(k_)                                                                \
-  do {                                                                            \
-    if (trw && it >= 6 && it < 10 && lane == 0) g_dbg_counters[trb + (k_)] = clock64(); \
-  } while (0)
-      AB_TRC(0);
       // one hand-off in: tiles of this step are in tensor memory (s_full), its vectors are staged (qdo_full)
       mbar_wait(&qdo_full[st], (it / AB_STAGES) & 1);
-      AB_TRC(1);
       mbar_wait(s_full, it & 1);
-      AB_TRC(2);
       tc_fence_after();
       const float* lse2 = sLse + st * AB_T + cq * 32;
       const float* dl = sDelta + st * AB_T + cq * 32;
@@ -439,7 +414,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tmem_ld32(tS + lane_off + cq * 32, ts);
       tmem_ld32(tDP + lane_off + cq * 32, tdp);
       tmem_ld_wait();
-      AB_TRC(3);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(sdp_free);  // S^T / dP^T of the next step may be issued while we do the math
@@ -468,13 +442,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         p[4 * q4 + 2] = r1.x;
         p[4 * q4 + 3] = r1.y;
       }
-      AB_TRC(4);
       // the previous step's dV MMAs must be done with this warp's P^T columns, its dK / dQ MMAs with its dS^T block
       if (it > 0) {
         mbar_wait(mma_done, (it - 1) & 1);
         tc_fence_after();
       }
-      AB_TRC(5);
       tmem_st16(tP + lane_off + cq * 16, w);
       store_bf16_row32(sDS + (cq >> 1) * AB_TILE + r * 128, r, (cq & 1) * 4, p);
       tmem_st_wait();
@@ -482,10 +454,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_ready);  // one hand-off out
-      AB_TRC(6);
-      if (tr_on && it >= 6 && it < 10 && lane == 0) g_dbg_counters[192 + (it - 6) * 16 + warp] = clock64();
-
-      AB_TRC(7);
       if (++st == AB_STAGES) st = 0;
     }
 
@@ -555,18 +523,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
 }  // namespace plm
 
-extern "C" int plm_debug_counters(unsigned long long* out, int32_t n, int32_t reset) {
-  if (!out || n <= 0 || n > 256) return plm::fail(PLM_ERR_INVALID, "debug_counters: bad argument");
-  cudaError_t e = cudaMemcpyFromSymbol(out, plm::g_dbg_counters, sizeof(unsigned long long) * n);
-  if (e != cudaSuccess) return plm::fail(PLM_ERR_CUDA, "debug_counters: %s", cudaGetErrorString(e));
-  if (reset) {
-    unsigned long long zeros[256] = {0};
-    e = cudaMemcpyToSymbol(plm::g_dbg_counters, zeros, sizeof(zeros));
-    if (e != cudaSuccess) return plm::fail(PLM_ERR_CUDA, "debug_counters reset: %s", cudaGetErrorString(e));
-  }
-  return PLM_OK;
-}
-
 extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                             const int32_t* seg_start, const float* rope_table, void* dqkv, float* delta,
                             float* dq_acc, int32_t B, int32_t T, int32_t H, int32_t hd, plm_stream_t stream_) {
@@ -613,7 +569,7 @@ extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, 
   dim3 grid((T + AB_T - 1) / AB_T, H, B);
   attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, seg_start, rope_table,
                                                          static_cast<__nv_bfloat16*>(dqkv), dq_acc, T, H, scale,
-                                                         scale * 1.4426950408889634f, getenv("PLM_ATTN_TRACE") ? 1 : 0);
+                                                         scale * 1.4426950408889634f);
   rc = check_launch("attn_bwd");
   if (rc != PLM_OK) return rc;
   {

@@ -13,7 +13,6 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
-#include <cstdlib>
 #include <mutex>
 
 namespace plm {
@@ -21,6 +20,12 @@ namespace plm {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+#ifdef PLM_GEMM_DEBUG
+#define PLM_DBG(p_) ((p_).debug)
+#else
+#define PLM_DBG(p_) 0
+#endif
 
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -39,9 +44,9 @@ struct GemmParams {
   int rope_cols, rope_T, head_dim;
   int glu_F;  // PLM_EPI_BF16_SWIGLU: F = N/2; tile n covers gate columns [128n, 128n+128) and up columns F + the same
   int num_m, num_n, kblocks;
-  int debug;      // diagnostics only (PLM_GEMM_DEBUG): 1 = skip epilogue operand loads, 2 = skip stores,
-                  // 4 = skip B tile loads, 8 = skip A tile loads, 16 = skip only the epilogue's global operand loads
-                  // (results are then garbage; timing experiments only)
+  int debug;      // only read when the library is compiled with -DPLM_GEMM_DEBUG (timing experiments: 1 = skip epilogue
+                  // operand loads, 2 = skip stores, 4 = skip B tile loads, 8 = skip A tile loads, 16 = skip only the
+                  // epilogue's global operand loads; results are then garbage).  Production builds fold it to 0.
   int n_fastest;  // tile rasterisation: 0 = consecutive tiles walk M (B tile reused), 1 = walk N (A tile reused)
 };
 
@@ -179,8 +184,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             continue;
           }
-          mbar_arrive_expect_tx(&full[s], ((p.debug & 8) ? 0 : Cfg::A_BYTES) + ((p.debug & 4) ? 0 : Cfg::B_BYTES));
-          if (p.debug & 8) {
+          mbar_arrive_expect_tx(&full[s], ((PLM_DBG(p) & 8) ? 0 : Cfg::A_BYTES) + ((PLM_DBG(p) & 4) ? 0 : Cfg::B_BYTES));
+          if (PLM_DBG(p) & 8) {
           } else if (A_K) {
             tma_load_2d(a_dst, &tmA, &full[s], kb * BK, m_blk * BM);
           } else {
@@ -188,7 +193,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int g = 0; g < BM / 64; ++g)
               tma_load_2d(a_dst + g * (BK * 128), &tmA, &full[s], m_blk * BM + g * 64, kb * BK);
           }
-          if (p.debug & 4) {
+          if (PLM_DBG(p) & 4) {
           } else if (CL == 1) {
             if (B_K && p.glu_F) {  // gate rows then up rows (the tensor map's box is BN/2 rows here)
               tma_load_2d(b_dst, &tmB, &full[s], kb * BK, n_blk * (BN / 2));
@@ -281,8 +286,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int r_tile = q * 32 + lane;          // row within the tile
     const bool elected = (threadIdx.x == 64);  // warp 2, lane 0 issues the bulk stores
     const bool out_bf16 = (p.epilogue == PLM_EPI_BF16 || p.epilogue == PLM_EPI_BF16_ROPE);
-    const bool is_rope = (p.epilogue == PLM_EPI_BF16_ROPE) && !(p.debug & 1);
-    const bool is_resid = (p.epilogue == PLM_EPI_RESID_F32) && !(p.debug & 1);
+    const bool is_rope = (p.epilogue == PLM_EPI_BF16_ROPE) && !(PLM_DBG(p) & 1);
+    const bool is_resid = (p.epilogue == PLM_EPI_RESID_F32) && !(PLM_DBG(p) & 1);
     const int piece = lane & 7;                // coalesced layout: 16-byte piece of a row's 128-byte segment
     const int lrow0 = q * 32 + (lane >> 3);    // ... of rows lrow0 + 4j, j = 0..7
     const uint32_t own_off = r_tile * 128;
@@ -305,7 +310,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       // coalesced fetch of sub-chunk `sc`'s global operand: dst[j] = piece `piece` of row lrow0 + 4j
       auto fetch_aux = [&](float4(&dst)[8], int sc) {
-        if (p.debug & 16) return;  // timing experiment: keep the staging + math, drop the global loads
+        if (PLM_DBG(p) & 16) return;  // timing experiment: keep the staging + math, drop the global loads
         const int64_t col0 = tile_col0 + sc * 32;
         if (is_resid) {
           const int64_t colp = col0 + piece * 4;
@@ -366,7 +371,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
           fence_proxy_async_smem();
           named_bar_sync(1, GEMM_EPI_WARPS * 32);
-          if (elected && !(p.debug & 2)) {
+          if (elected && !(PLM_DBG(p) & 2)) {
             tma_store_2d(map, buf, c0, r0);
             bulk_commit_group();
           }
@@ -465,7 +470,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
           fence_proxy_async_smem();
           named_bar_sync(1, GEMM_EPI_WARPS * 32);
-          if (elected && !(p.debug & 2)) {
+          if (elected && !(PLM_DBG(p) & 2)) {
             tma_store_2d(&tmC, buf, static_cast<int>(tile_col0) + c * 64, r0);
             bulk_commit_group();
           }
@@ -514,7 +519,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           fence_proxy_async_smem();
           named_bar_sync(1, GEMM_EPI_WARPS * 32);
-          if (elected && !(p.debug & 2)) {
+          if (elected && !(PLM_DBG(p) & 2)) {
             const int c0 = static_cast<int>(tile_col0) + sc * 32;
             if (p.epilogue == PLM_EPI_ATOMIC_F32)
               tma_reduce_add_2d(&tmC, buf, c0, r0);
@@ -572,12 +577,30 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return check_launch("gemm_kernel");
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
+// Tuning overrides for A/B measurements (tools/gpu_kernel_check.py, tests): process-global, set through
+// plm_gemm_set_tuning(), never read from the environment on the launch path.  Defaults = automatic choices.
+struct GemmTuning {
+  int bn = 0;        // 128 / 256 forces the tile width
+  int raster = -1;   // 0 / 1 forces the tile walk order
+  int cluster = 0;   // 1 / 2 forces the cluster size
+  int pair = 1;      // 0: two cta_group::1 MMAs sharing a multicast B tile instead of the CTA-pair MMA
+  int debug = 0;     // only honoured by -DPLM_GEMM_DEBUG builds
+};
+static GemmTuning g_gemm_tuning;
+static const GemmTuning& gemm_env() { return g_gemm_tuning; }
 
 }  // namespace plm
+
+extern "C" int plm_gemm_set_tuning(int32_t bn, int32_t raster, int32_t cluster, int32_t pair, int32_t debug) {
+  if (!(bn == 0 || bn == 128 || bn == 256) || raster < -1 || raster > 1 || cluster < 0 || cluster > 2)
+    return plm::fail(PLM_ERR_INVALID, "gemm_set_tuning: bad value");
+  plm::g_gemm_tuning.bn = bn;
+  plm::g_gemm_tuning.raster = raster;
+  plm::g_gemm_tuning.cluster = cluster;
+  plm::g_gemm_tuning.pair = pair;
+  plm::g_gemm_tuning.debug = debug;
+  return PLM_OK;
+}
 
 extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   using namespace plm;
@@ -621,7 +644,7 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   p.rope_T = a->rope_T;
   p.head_dim = a->head_dim;
   p.glu_F = glu ? static_cast<int>(a->N / 2) : 0;
-  p.debug = env_int("PLM_GEMM_DEBUG", 0);
+  p.debug = gemm_env().debug;
   p.kblocks = static_cast<int>((a->K + BK - 1) / BK);
   p.num_m = static_cast<int>((a->M + BM - 1) / BM);
 
@@ -634,7 +657,7 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   // 16384 x 1024 x 1024)
   if (a->epilogue == PLM_EPI_RESID_F32 && a->K <= 1024) bn = 128;
   {
-    const int forced = env_int("PLM_GEMM_BN", 0);
+    const int forced = gemm_env().bn;
     if (forced == 128 || forced == 256) bn = forced;
   }
   if (glu) bn = 256;  // 128 gate + 128 up columns per tile
@@ -645,14 +668,14 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
     const double b_bytes = 2.0 * static_cast<double>(a->N) * static_cast<double>(a->K);
     p.n_fastest = (b_bytes < a_bytes) ? 1 : 0;  // measured with CTA pairs: walking N wins whenever the weights are the
                                                 // smaller operand (fc1 151 -> 147 us, out-proj 55 -> 52 us), even if A fits in L2
-    const int forced = env_int("PLM_GEMM_RASTER", -1);
+    const int forced = gemm_env().raster;
     if (forced == 0 || forced == 1) p.n_fastest = forced;
   }
   p.num_n = static_cast<int>((a->N + bn - 1) / bn);
   // 2-CTA clusters (M-adjacent tiles sharing a multicast B tile) whenever there is more than one M block
   int cl = (p.num_m >= 2 && bn == 256) ? 2 : 1;
   {
-    const int forced = env_int("PLM_GEMM_CLUSTER", 0);
+    const int forced = gemm_env().cluster;
     if (forced == 1 || (forced == 2 && bn == 256)) cl = forced;
   }
 
@@ -714,7 +737,7 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   return launch_gemm<BN_, false, false, CL_>(tmA, tmB, tmC, tmC2, p, stream);
   // CTA-pair MMA (tcgen05.mma.cta_group::2) for every clustered launch; PLM_GEMM_PAIR=0 falls back to two
   // cta_group::1 MMAs sharing a multicast B tile
-  const bool pair = cl == 2 && bn == 256 && env_int("PLM_GEMM_PAIR", 1) != 0;
+  const bool pair = cl == 2 && bn == 256 && gemm_env().pair != 0;
   if (pair) {
     if (a_k && b_k) return launch_gemm<256, true, true, 2, true>(tmA, tmB, tmC, tmC2, p, stream);
     if (a_k && !b_k) return launch_gemm<256, true, false, 2, true>(tmA, tmB, tmC, tmC2, p, stream);

@@ -174,6 +174,13 @@ sumsq_final_kernel(const float* __restrict__ partial, int nblocks, float* __rest
 }
 
 // ------------------------------------------------------------------------------------------- optimizers
+// Non-finite gradients never reach the master weights: when the squared gradient norm handed to an update kernel is
+// NaN or Inf (a NaN loss makes every gradient NaN), the kernel leaves p, the optimizer state and the bf16 shadow
+// untouched.  The host raises the reference's 'Train loss is nan' (engine/engine.py:116-117) at its next check.
+__device__ __forceinline__ bool grads_poisoned(const float* gnorm_sq) {
+  return gnorm_sq != nullptr && !isfinite(*gnorm_sq);
+}
+
 __device__ __forceinline__ float clip_coef(const float* gnorm_sq, float max_norm) {
   if (gnorm_sq == nullptr || max_norm <= 0.f) return 1.0f;
   const float norm = sqrtf(*gnorm_sq);
@@ -196,6 +203,7 @@ __device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              __nv_bfloat16* __restrict__ pb, int64_t n, AdamArgs a, const float* __restrict__ gnorm_sq) {
+  if (grads_poisoned(gnorm_sq)) return;
   const float clip = clip_coef(gnorm_sq, a.max_norm);
   const int64_t n4 = n >> 2;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -243,6 +251,7 @@ __global__ void __launch_bounds__(256)
 signsgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                __nv_bfloat16* __restrict__ pb, int64_t n, float lr, float mu, float omd, float decay, int first,
                const float* __restrict__ gnorm_sq, float max_norm) {
+  if (grads_poisoned(gnorm_sq)) return;
   const float clip = clip_coef(gnorm_sq, max_norm);
   const int64_t n4 = n >> 2;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -309,6 +318,7 @@ template <class Op, bool HAS_V>
 __global__ void __launch_bounds__(256)
 flat_opt_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 __nv_bfloat16* __restrict__ pb, int64_t n, Op op, float max_norm, const float* __restrict__ gnorm_sq) {
+  if (grads_poisoned(gnorm_sq)) return;
   const float clip = clip_coef(gnorm_sq, max_norm);
   const int64_t n4 = n >> 2;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;

@@ -37,25 +37,29 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~the hint (ns)
+// elapses.  Without the hint a failed try returns after a few hundred cycles, and a waiting warp turns into a spin
+// loop that competes for issue slots with the warps doing the math: in the round-1 attention backward 36 % of all
+// executed instructions were such polling loops (profiles/r2_attn_bwd_instruction_mix.md).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
       : "memory");
   return ok != 0;
 }
-// Spins until the phase with the given parity has completed.  A protocol bug must not hang the GPU: after ~4 s of
+// Waits until the phase with the given parity has completed.  A protocol bug must not hang the GPU: after ~4 s of
 // failed tries the thread traps (the launch then fails with an error instead of never returning).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t tries = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++tries & 0xfffu) == 0 && clock64() - t0 > 8000000000ll) __trap();
+    if ((++tries & 0x3fu) == 0 && clock64() - t0 > 8000000000ll) __trap();
   }
 }
 // Arrive on the barrier at the same smem offset in CTA `cta_rank` of this cluster.

@@ -35,11 +35,14 @@ class GradReducer:
     self.wire = torch.empty(flat.total, device=flat.grads.device, dtype=wire_dtype)
     self.wire_dtype = wire_dtype
     self.on_cuda = flat.grads.is_cuda
-    self.pack = pack or (lambda s, d, sc: ops.cast_f32_bf16(s, d, sc))
-    self.unpack = unpack or (lambda s, d, sc: ops.cast_bf16_f32(s, d, sc))
-    if wire_dtype == torch.float32:  # A/B switch: the reference's fp32 wire format
-      self.pack = lambda s, d, sc: d.copy_(s).mul_(sc)
-      self.unpack = lambda s, d, sc: d.copy_(s)
+    if wire_dtype == torch.float32:  # cfg key `ddp_fp32_allreduce: True`: the reference DDP's fp32 wire format
+      default_pack = lambda s, d, sc: d.copy_(s).mul_(sc)  # noqa: E731
+      default_unpack = lambda s, d, sc: d.copy_(s)  # noqa: E731
+    else:  # BASELINE north_star: bf16 on the wire (pre-scaled by 1/world before rounding)
+      default_pack = lambda s, d, sc: ops.cast_f32_bf16(s, d, sc)  # noqa: E731
+      default_unpack = lambda s, d, sc: ops.cast_bf16_f32(s, d, sc)  # noqa: E731
+    self.pack = pack or default_pack  # caller-injected functions (CPU/gloo tests) always win
+    self.unpack = unpack or default_unpack
     self.comm_stream = torch.cuda.Stream(device=flat.grads.device) if self.on_cuda else None
     self._pending = []
     self.launched = 0

@@ -9,8 +9,12 @@ What changes underneath (SURVEY.md §3.2 -> here):
     of an accumulation cycle (reference: engine.py:104-105);
   * clip_grad_norm_ + optimizer.step() is one reduction pass + one flat update kernel, clip coefficient computed on
     the device (no host sync);
-  * the per-micro-step `isnan` host sync (reference: engine.py:116) is kept in meaning but deferred: the loss is
-    copied to pinned memory asynchronously and checked at the next call (or by `check_nan()`).
+  * the per-micro-step `isnan` host sync (reference: engine.py:116) is kept in meaning but moved: every micro-step's
+    loss is copied to its own pinned slot asynchronously, and ALL slots of the accumulation cycle are checked (one host
+    sync) at the accumulation boundary BEFORE the optimizer update — a NaN loss raises before any weight, moment or
+    bf16 shadow changes, exactly as in the reference.  Independently the update kernels skip themselves on the device
+    when the gradient norm is not finite, so a poisoned gradient cannot reach the master weights even if the caller
+    swallows the exception.
 """
 
 import torch
@@ -104,9 +108,9 @@ class TorchEngine(torch.nn.Module):
     self._staging = _HostStaging(dev)
     self._sumsq_ws = sumsq_workspace(dev)
     self._gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
-    self._loss_host = torch.zeros(2, dtype=torch.float32, pin_memory=True)
-    self._loss_events = [None, None]
-    self._loss_slot = 0
+    n_slots = max(int(self.accumulation_steps), 1)  # one pinned slot per micro-step of an accumulation cycle
+    self._loss_host = torch.zeros(n_slots, dtype=torch.float32, pin_memory=True)
+    self._loss_events = [None] * n_slots
 
   # ------------------------------------------------------------------------------------------ batch staging
   def _move_to_device(self, batch):
@@ -128,25 +132,32 @@ class TorchEngine(torch.nn.Module):
     return inputs, targets, seg
 
   # ------------------------------------------------------------------------------------------ NaN guard
-  def _record_loss(self, loss):
-    k = self._loss_slot
+  def _record_loss(self, loss, k):
+    """Queue the device->host copy of micro-step k's loss (k = index inside the accumulation cycle).  A slot is only
+    reused after check_nan(wait=True) has consumed it at the accumulation boundary."""
+    if self._loss_events[k] is not None:  # defensive: never overwrite an unchecked loss
+      self._loss_events[k].synchronize()
+      self._consume_loss(k)
     self._loss_host[k : k + 1].copy_(loss.reshape(1), non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
     self._loss_events[k] = ev
-    self._loss_slot = 1 - k
+
+  def _consume_loss(self, k):
+    self._loss_events[k] = None
+    if torch.isnan(self._loss_host[k]):
+      raise ValueError('Train loss is nan')
 
   def check_nan(self, wait=False):
-    """Raise ValueError('Train loss is nan') (reference: engine.py:116-117) for any completed micro-step."""
+    """Raise ValueError('Train loss is nan') (reference: engine.py:116-117) for any completed micro-step; with
+    wait=True, for every micro-step launched so far (one host sync)."""
     for k, ev in enumerate(self._loss_events):
       if ev is None:
         continue
       if wait:
         ev.synchronize()
       if ev.query():
-        self._loss_events[k] = None
-        if torch.isnan(self._loss_host[k]):
-          raise ValueError('Train loss is nan')
+        self._consume_loss(k)
 
   # ------------------------------------------------------------------------------------------ train step
   def step(self, batch):
@@ -171,16 +182,17 @@ class TorchEngine(torch.nn.Module):
     else:  # the data-parallel micro-step interleaves NCCL buckets with backward: launched eagerly
       loss_val = self.rt.loss_and_backward(inputs, targets, seg_start, grad_scale=1.0 / self.accumulation_steps,
                                            backward=True, on_bucket=on_bucket)
-    self._record_loss(loss_val)
+    self._record_loss(loss_val, self.accumulated_samples - 1)
 
     if last:
       self.accumulated_samples = 0
       if self.reducer is not None:
         self.reducer.finish()
-      clip = None
-      if self.grad_clip:
-        grad_sumsq(self.rt.flat, self._sumsq_ws, self._gnorm_sq)
-        clip = GradClip(self._gnorm_sq, self.grad_clip)
+      # the gradient norm is always computed (4 B/param): it clips when grad_clip is set (max_norm > 0) and, clip or
+      # not, gates the update kernels on the device (non-finite norm -> no update)
+      grad_sumsq(self.rt.flat, self._sumsq_ws, self._gnorm_sq)
+      clip = GradClip(self._gnorm_sq, self.grad_clip or 0.0)
+      self.check_nan(wait=True)  # reference: raise before optimizer.step (engine.py:116-117 precedes :131)
       self.optimizer.step(grad_clip=clip)
       if self.scheduler:
         self.scheduler.step()

@@ -176,12 +176,17 @@ class TrainRuntime:
     self.L = L
 
   def workspace(self, B, T):
+    """At most two shapes stay alive (train + eval).  Eviction is least-recently-used and never takes a workspace that
+    holds captured CUDA graphs (the training shape) while another candidate exists."""
     key = (B, T)
-    if key not in self._ws:
-      if len(self._ws) >= 2:  # keep at most two shapes alive (train + eval)
-        self._ws.pop(next(iter(self._ws)))
-      self._ws[key] = _Workspace(self, B, T)
-    return self._ws[key]
+    ws = self._ws.pop(key, None)
+    if ws is None:
+      if len(self._ws) >= 2:
+        victims = [k for k, w in self._ws.items() if not w.graphs] or list(self._ws)
+        self._ws.pop(victims[0])
+      ws = _Workspace(self, B, T)
+    self._ws[key] = ws  # re-insert: dict order = recency
+    return ws
 
   # ------------------------------------------------------------------------------------------ forward
   def forward_hidden(self, ids, seg_start, ws):
@@ -245,8 +250,8 @@ class TrainRuntime:
       ws.seg.copy_(seg_start.reshape(-1), non_blocking=True)
     key = (masked, float(grad_scale))
     rec = ws.graphs.get(key)
+    seg = ws.seg if masked else None
     if rec is None:
-      seg = ws.seg if masked else None
       cur = torch.cuda.current_stream()
       side = torch.cuda.Stream()
       side.wait_stream(cur)
@@ -255,14 +260,24 @@ class TrainRuntime:
         self._micro_step(ws, seg, grad_scale)  # warm-up: lazy one-time initialisation happens outside the capture
         graph = torch.cuda.CUDAGraph()
         n0 = ops.LAUNCHES
-        with torch.cuda.graph(graph, stream=side):
-          self._micro_step(ws, seg, grad_scale)
-        launches = ops.LAUNCHES - n0
+        try:
+          # thread_local: only THIS thread's illegal calls invalidate the capture.  The reference's DataLoader runs
+          # with pin_memory=True (data/dataloaders.py), whose pin-memory thread calls cudaHostAlloc at any time; under
+          # the default 'global' mode that would abort the capture (or make the pin thread fail).
+          with torch.cuda.graph(graph, stream=side, capture_error_mode='thread_local'):
+            self._micro_step(ws, seg, grad_scale)
+          rec = (graph, ops.LAUNCHES - n0)
+        except RuntimeError as e:  # capture refused: run this (shape, mask, scale) eagerly from now on
+          print(f'plainlm_b200: CUDA graph capture failed ({str(e).splitlines()[0]}); falling back to eager launches')
+          self._readers.clear()
+          rec = 'eager'
         self.flat.grads.copy_(saved)
         del saved
       cur.wait_stream(side)
-      rec = (graph, launches)
       ws.graphs[key] = rec
+    if rec == 'eager':
+      self._micro_step(ws, seg, grad_scale)
+      return ws.stats[2].clone()
     graph, launches = rec
     graph.replay()
     ops.LAUNCHES += launches
@@ -311,7 +326,8 @@ class TrainRuntime:
     def done(on_side=False):
       nonlocal bucket
       if on_bucket is not None:
-        if on_side:  # the bucket is final when the side-stream wgrads are: let the reducer record its event there
+        if on_side and not os.environ.get('PLM_NO_SIDE_STREAM'):
+          # the bucket is final when the side-stream wgrads are: let the reducer record its event there
           with torch.cuda.stream(self.wstream):
             on_bucket(bucket)
         else:

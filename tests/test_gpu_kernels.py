@@ -49,9 +49,10 @@ def test_gemm_operand_majors(a_k, b_k, M, N, K):
 
 
 @pytest.mark.parametrize('bn', [128, 256])
-def test_gemm_epilogues(bn, monkeypatch):
+def test_gemm_epilogues(bn, request):
   ops, _lib = _ops()
-  monkeypatch.setenv('PLM_GEMM_BN', str(bn))
+  _lib.gemm_tuning(bn=bn)  # force the tile width (diagnostic override; restored below)
+  request.addfinalizer(_lib.gemm_tuning)
   g = torch.Generator().manual_seed(5)
   M, N, K, T, hd = 256, 768, 256, 128, 64
   A = (torch.randn(M, K, generator=g) * 0.5).to(bf16)

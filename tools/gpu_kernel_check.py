@@ -57,7 +57,7 @@ def case_gemm(M, N, K, a_k, b_k, epi='bf16', bn=0, splits=1):
   from plainlm_b200 import ops, _lib
 
   if bn:
-    os.environ['PLM_GEMM_BN'] = str(bn)
+    _lib.gemm_tuning(bn=bn)
   torch.manual_seed(0)
   dev = 'cuda'
   A = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)  # logical [M,K]
@@ -395,11 +395,9 @@ def case_gemm_perf():
       rec = {'case': f'{name} {vname} M{M} N{n} K{k}'}
       for cl in (1, 2):
         for raster in (0, 1):
-          os.environ['PLM_GEMM_CLUSTER'] = str(cl)
-          os.environ['PLM_GEMM_RASTER'] = str(raster)
+          _lib.gemm_tuning(cluster=cl, raster=raster)
           rec[f'cl{cl}_r{raster}'] = round(flops / _time(fn, 6) / 1e9, 0)
-      os.environ.pop('PLM_GEMM_CLUSTER')
-      os.environ.pop('PLM_GEMM_RASTER')
+      _lib.gemm_tuning()
       rec['auto'] = round(flops / _time(fn, 6) / 1e9, 0)
       rec['cublas'] = round(flops / _time(cublas[vname], 6) / 1e9, 0)
       out.append(rec)
@@ -412,7 +410,7 @@ def case_gemm_sustained():
   import subprocess as sp
   import statistics
   import torch
-  from plainlm_b200 import ops
+  from plainlm_b200 import ops, _lib
 
   dev = 'cuda'
   M, n, k = 16384, 5632, 1024
@@ -421,11 +419,11 @@ def case_gemm_sustained():
   y = torch.empty(M, n, device=dev, dtype=torch.bfloat16)
   flops = 2.0 * M * n * k
   out = []
-  variants = [('ours_cl2', lambda: ops.gemm(x, w, y), {'PLM_GEMM_CLUSTER': '2'}),
-              ('ours_cl1', lambda: ops.gemm(x, w, y), {'PLM_GEMM_CLUSTER': '1'}),
+  variants = [('ours_cl2', lambda: ops.gemm(x, w, y), {'cluster': 2}),
+              ('ours_cl1', lambda: ops.gemm(x, w, y), {'cluster': 1}),
               ('cublas', lambda: torch.matmul(x, w.t(), out=y), {})]
   for name, fn, env in variants:
-    os.environ.update(env)
+    _lib.gemm_tuning(**env)
     for _ in range(20):
       fn()
     torch.cuda.synchronize()
@@ -445,8 +443,7 @@ def case_gemm_sustained():
     ms = e0.elapsed_time(e1) / iters
     out.append({'case': f'sustained fc1 fwd {name}', 'tflops': round(flops / ms / 1e9, 0), 'secs': round(ms * iters / 1e3, 2),
                 'sm_mhz_median': statistics.median(clk) if clk else None, 'power_w_median': statistics.median(pw) if pw else None})
-    for kk in env:
-      os.environ.pop(kk)
+    _lib.gemm_tuning()
   return out
 
 
@@ -479,19 +476,19 @@ def case_gemm_epi_perf():
     ('swiglu alone', lambda: ops.swiglu_fwd(u, g), 2.0 * M * d * 2 * F),
   ]
   results = []
-  for dbg in (0, 1, 2, 3, 16):
-    os.environ['PLM_GEMM_DEBUG'] = str(dbg)
+  for dbg in (0, 1, 2, 3, 16):  # masks other than 0 only act in a -DPLM_GEMM_DEBUG build of the library
+    _lib.gemm_tuning(debug=dbg)
     for n, fn, fl in cases:
       ms = _time(fn, 10)
       results.append({'case': f'{n} dbg{dbg}', 'ms': round(ms, 4), 'tflops': round(fl / ms / 1e9, 0)})
-  os.environ.pop('PLM_GEMM_DEBUG')
+  _lib.gemm_tuning()
   return results
 
 
 def case_gemm_feed_probe():
   """Is the main loop bound by operand delivery?  Store-less runs with the A and/or B tile loads removed."""
   import torch
-  from plainlm_b200 import ops
+  from plainlm_b200 import ops, _lib
 
   dev = 'cuda'
   M, d, F = 16384, 1024, 2816
@@ -506,15 +503,13 @@ def case_gemm_feed_probe():
     ('fc1 dgrad', lambda: ops.gemm(du, w1, dx, a_kmajor=True, b_kmajor=False), 2.0 * M * 2 * F * d),
   ]
   results = []
-  for cl in ('2', '1'):
-    os.environ['PLM_GEMM_CLUSTER'] = cl
+  for cl in (2, 1):
     for dbg in (0, 2, 6, 10, 14):
-      os.environ['PLM_GEMM_DEBUG'] = str(dbg)
+      _lib.gemm_tuning(cluster=cl, debug=dbg)
       for n, fn, fl in cases:
         ms = _time(fn, 10)
         results.append({'case': f'{n} cl{cl} dbg{dbg}', 'ms': round(ms, 4), 'tflops': round(fl / ms / 1e9, 0)})
-  os.environ.pop('PLM_GEMM_DEBUG')
-  os.environ.pop('PLM_GEMM_CLUSTER')
+  _lib.gemm_tuning()
   return results
 
 
@@ -540,12 +535,12 @@ def case_gemm_n1024_probe():
       fn = (lambda a=a, b=b: ops.gemm(a, b, outb, a_kmajor=True, b_kmajor=False))
     shapes.append((name, fn, 2.0 * M * d * K))
   results = []
-  for bn in ('256', '128'):
-    os.environ['PLM_GEMM_BN'] = bn
+  for bn in (256, 128):
+    _lib.gemm_tuning(bn=bn)
     for n, fn, fl in shapes:
       ms = _time(fn, 10)
       results.append({'case': f'{n} bn{bn}', 'ms': round(ms, 4), 'tflops': round(fl / ms / 1e9, 0)})
-  os.environ.pop('PLM_GEMM_BN')
+  _lib.gemm_tuning()
   return results
 
 
@@ -601,56 +596,6 @@ def case_bw_perf():
   return out
 
 
-def case_attn_bwd_trace():
-  """clock64 timeline of one attention-backward CTA (PLM_ATTN_TRACE): where a steady-state step spends its cycles."""
-  import ctypes
-  import torch
-  from plainlm_b200 import ops, _lib
-
-  dev = 'cuda'
-  B, T, H, hd = 8, 2048, 16, 64
-  d = H * hd
-  qkv = torch.randn(B * T, 3 * d, device=dev).to(torch.bfloat16)
-  out = torch.empty(B * T, d, device=dev, dtype=torch.bfloat16)
-  lse = torch.empty(B, H, T, device=dev)
-  dout = torch.randn(B * T, d, device=dev).to(torch.bfloat16)
-  dqkv = torch.empty(B * T, 3 * d, device=dev, dtype=torch.bfloat16)
-  delta = torch.empty(B, H, T, device=dev)
-  dq_acc = torch.empty(B * T, d, device=dev)
-  ops.attn_fwd(qkv, out, lse, B, T, H, hd)
-  for _ in range(2):
-    ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd)
-  os.environ['PLM_ATTN_TRACE'] = '1'
-  ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd)
-  os.environ.pop('PLM_ATTN_TRACE')
-  torch.cuda.synchronize()
-  buf = (ctypes.c_ulonglong * 256)()
-  _lib.check(_lib.load().plm_debug_counters(buf, 256, 1), 'plm_debug_counters')
-  v = list(buf)
-  t0 = v[0]
-  ev = []
-  names = {0: 'C0', 160: 'C15', 64: 'iS', 96: 'iDV', 128: 'iDK'}
-  labels = {
-    'C0': ['top', 'qdo_full', 's_full', 'tmem_ld done', 'math done', 'dv_done/dq_full', 'pds_ready sent', 'dq flushed'],
-    'C15': ['top', 'qdo_full', 's_full', 'tmem_ld done', 'math done', 'dv_done/dq_full', 'pds_ready sent', 'dq flushed'],
-    'iS': ['qdo_full', 'sdp_free', 'S/dP issued', 'dQ(it-1) issued'], 'iDV': ['pds_ready', 'dV issued', '-', '-'],
-    'iDK': ['pds_ready', 'dK issued', '-', '-'],
-  }
-  for base, nm in names.items():
-    per = 8 if nm.startswith('C') else 4
-    for itr in range(4):
-      for k in range(per):
-        t = v[base + itr * per + k]
-        if t:
-          ev.append((t - t0, f'{nm} it{6 + itr} {labels[nm][k]}'))
-  for itr in range(4):
-    ws = [v[192 + itr * 16 + w] - t0 for w in range(16) if v[192 + itr * 16 + w]]
-    if ws:
-      ev.append((max(ws), f'ALL it{6 + itr} pds_ready sent by the last warp (first {min(ws)})'))
-  ev.sort()
-  return [{'case': 'timeline', 'events': [f'{t:7d} {n}' for t, n in ev]}]
-
-
 def case_attn_perf():
   import torch
   from plainlm_b200 import ops
@@ -673,6 +618,9 @@ def case_attn_perf():
     ('attn_fwd variant 0', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant=0), flops_fwd),
     ('attn_fwd variant 1', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant=1), flops_fwd),
     ('attn_fwd variant 2', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant=2), flops_fwd),
+    ('attn_fwd variant 10', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant=10), flops_fwd),
+    ('attn_fwd variant 11', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant=11), flops_fwd),
+    ('attn_fwd variant 12', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant=12), flops_fwd),
     ('attn_bwd', lambda: ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd), 2.5 * flops_fwd),
   ):
     for _ in range(3):
@@ -729,6 +677,16 @@ CASES['attn_fwd_peaky'] = lambda: case_attn_fwd(2, 512, 2, scale=4.0)   # large 
 CASES['attn_fwd_peaky_v2'] = lambda: case_attn_fwd(2, 512, 2, scale=4.0, variant=2)
 CASES['attn_fwd_doc'] = lambda: case_attn_fwd(2, 512, 2, doc=True)
 CASES['attn_fwd_doc_v2'] = lambda: case_attn_fwd(2, 512, 2, doc=True, variant=2)
+for _v in (10, 11, 12):
+  CASES[f'attn_fwd3_1tile_v{_v}'] = lambda v=_v: case_attn_fwd(1, 128, 1, variant=v)
+  CASES[f'attn_fwd3_2tile_v{_v}'] = lambda v=_v: case_attn_fwd(1, 256, 1, variant=v)
+  CASES[f'attn_fwd3_4tile_v{_v}'] = lambda v=_v: case_attn_fwd(1, 512, 2, variant=v)
+  CASES[f'attn_fwd3_ragged_v{_v}'] = lambda v=_v: case_attn_fwd(2, 200, 2, variant=v)
+  CASES[f'attn_fwd3_multi_v{_v}'] = lambda v=_v: case_attn_fwd(2, 640, 3, variant=v)
+  CASES[f'attn_fwd3_peaky_v{_v}'] = lambda v=_v: case_attn_fwd(2, 512, 2, scale=4.0, variant=v)
+  CASES[f'attn_fwd3_doc_v{_v}'] = lambda v=_v: case_attn_fwd(2, 512, 2, doc=True, variant=v)
+  CASES[f'attn_fwd3_many_items_v{_v}'] = lambda v=_v: case_attn_fwd(3, 1024, 40, variant=v)
+  CASES[f'attn_fwd3_long_v{_v}'] = lambda v=_v: case_attn_fwd(1, 4096, 2, variant=v)
 CASES['attn_fwd_many_items'] = lambda: case_attn_fwd(3, 1024, 40)  # 480 items: several rounds of the persistent schedule
 CASES['attn_fwd_long'] = lambda: case_attn_fwd(1, 4096, 2)
 CASES['attn_bwd_1tile'] = lambda: case_attn_bwd(1, 128, 1)
@@ -742,7 +700,6 @@ CASES['bw_perf'] = case_bw_perf
 CASES['gemm_epi_perf'] = case_gemm_epi_perf
 CASES['gemm_feed_probe'] = case_gemm_feed_probe
 CASES['gemm_n1024_probe'] = case_gemm_n1024_probe
-CASES['attn_bwd_trace'] = case_attn_bwd_trace
 CASES['gemm_sustained'] = case_gemm_sustained
 
 

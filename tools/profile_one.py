@@ -21,8 +21,10 @@ if which == 'attn':
   dqkv = torch.empty(M, 3 * d, device=dev, dtype=bf)
   delta = torch.empty(B, H, T, device=dev)
   dq_acc = torch.empty(M, d, device=dev)
+  variants = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [None]
   for _ in range(2):
-    ops.attn_fwd(qkv, out, lse, B, T, H, hd)
+    for v in variants:
+      ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant=v)
     ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd)
 elif which == 'gemm':
   x = torch.randn(M, d, device=dev).to(bf)
