@@ -4,7 +4,7 @@ This file restates, function by function, the arithmetic of the reference's hot 
 (Niccolo-Ajroldi/plainLM: engine/engine.py:93-141 -> models/transformer.py -> optim) as explicit torch-CPU code, so
 that the CUDA path in plainlm_b200/ can be checked against it on a machine where /root/reference does not exist.
 It is imported ONLY by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; nothing
-under plainlm_b200/ may import it (tests/test_no_oracle_in_product.py enforces that).
+under plainlm_b200/ may import it (tests/test_host_logic.py::test_product_never_imports_the_oracle enforces that).
 
 Parity status: PINNED.  tests/golden/make_golden.py imports the real reference from /root/reference in the build
 container, runs it (TORCHDYNAMO_DISABLE=1, CPU, fp32 and bf16-autocast) and commits its outputs as fixtures under

@@ -468,28 +468,38 @@ static int launch_attn_fwd(const CUtensorMap& tm, const int32_t* seg_start, void
 // 16 warps: 0..11 softmax (stream = warp / 4), 12..14 one MMA issuer per stream, 15 TMA producer.  512 threads leave
 // 128 registers per thread: no setmaxnreg.
 constexpr int A3_STREAMS = 3;
-constexpr int A3_STAGES = 6;
+constexpr int A3_STAGES = 10;  // deep enough for a stream to run 4+ subtiles ahead of the slowest one (see rotation)
 constexpr int A3_W_ISSUE = 4 * A3_STREAMS;   // warps 12, 13, 14
 constexpr int A3_W_TMA = A3_W_ISSUE + A3_STREAMS;  // warp 15
 constexpr int A3_THREADS = (A3_W_TMA + 1) * 32;
 constexpr int A3_OFF_RING = A3_STREAMS * AF_QTILE_BYTES;
 constexpr int A3_OFF_BARS = A3_OFF_RING + A3_STAGES * AF_STAGE_BYTES;
-constexpr int A3_NBARS = 2 * A3_STAGES + 7 * A3_STREAMS;
-constexpr int A3_SMEM = A3_OFF_BARS + A3_NBARS * 8 + 16;
+constexpr int A3_NBARS = 2 * A3_STAGES + 7 * A3_STREAMS + 8;  // + 2 grant barriers per scheduler (MUFU lock)
+constexpr int A3_SMEM = A3_OFF_BARS + A3_NBARS * 8 + 16 + 16;  // + tmem slot + 4 ticket counters
 constexpr int A3_TCOLS = 160;  // TMEM columns per stream: S at +0, P at +64, O at +96
 
 struct A3Item {
   int b, h, t0;   // first query tile of the group
   int j_lo;       // first 64-key subtile any row of the item can see
   int cnt;        // active streams (query tiles) of the item: 1..3
+  int rot;        // stream s works on tile t0 + (s + rot) % cnt: the longest tile of a group rotates over the streams
   int n_ring;     // subtiles the producer loads = subtiles of the item's last tile
   int64_t row0;   // global row of the item's first query
 };
 struct A3Sched {
   int n_items, BH, H, T, nq;
 };
-// subtiles stream s of the item consumes (0: inactive)
-__device__ __forceinline__ int a3_n(const A3Item& it, int s) { return s < it.cnt ? 2 * (it.t0 + s) + 2 - it.j_lo : 0; }
+// position (tile index within the group) stream s works on, -1: inactive.  A group's tiles need n, n + 2, n + 4
+// subtiles; with a fixed assignment stream 2 would do 4 subtiles more than stream 0 in EVERY item and the others would
+// idle 12 % of the time.  Rotating the assignment with the item counter equalises the streams' totals, and the deep
+// (K, V) ring lets a stream that finished its tile run ahead into the next item instead of waiting.
+__device__ __forceinline__ int a3_pos(const A3Item& it, int s) {
+  if (s >= it.cnt) return -1;
+  const int p = s + it.rot;
+  return p >= it.cnt ? p - it.cnt : p;
+}
+// subtiles the tile at position `pos` consumes (0: inactive)
+__device__ __forceinline__ int a3_n(const A3Item& it, int pos) { return pos >= 0 ? 2 * (it.t0 + pos) + 2 - it.j_lo : 0; }
 
 // k-th item of this CTA in the snake order over the heaviest-first item list (groups are cut from the END of the
 // sequence, so only the lightest group of a (batch, head) can be short); false when the list is exhausted.
@@ -504,6 +514,7 @@ __device__ __forceinline__ bool a3_item(const A3Sched& sc, int k, const int32_t*
   const int lo = sc.nq - A3_STREAMS * (g + 1);
   it.t0 = lo < 0 ? 0 : lo;
   it.cnt = lo < 0 ? A3_STREAMS + lo : A3_STREAMS;
+  it.rot = it.cnt == A3_STREAMS ? k % A3_STREAMS : 0;
   it.row0 = static_cast<int64_t>(it.b) * sc.T + static_cast<int64_t>(it.t0) * AF_BQ;
   it.j_lo = seg_start ? (__ldg(seg_start + it.row0) / AF_BK) : 0;
   it.n_ring = 2 * (it.t0 + it.cnt - 1) + 2 - it.j_lo;
@@ -527,7 +538,9 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
   uint64_t* p_full = q_full + 4 * A3_STREAMS;      //      P of the subtile is in tensor memory (4 warps)
   uint64_t* pv_done = q_full + 5 * A3_STREAMS;     //      the subtile's P·V has completed: P may be overwritten, O read
   uint64_t* o_free = q_full + 6 * A3_STREAMS;      //      the epilogue has read O (4 warps)
+  uint64_t* grant = q_full + 7 * A3_STREAMS;       // [4 schedulers][2]  MUFU lock, see softmax warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + A3_NBARS);
+  uint32_t* ticket = tmem_slot + 1;                // [4]
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
@@ -557,7 +570,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
       mbar_init(&pv_done[i], 1);
       mbar_init(&o_free[i], 4);
     }
+    for (int i = 0; i < 8; ++i) mbar_init(&grant[i], 1);
+    for (int i = 0; i < 4; ++i) ticket[i] = 0;
     fence_barrier_init();
+    for (int i = 0; i < 4; ++i) mbar_arrive(&grant[2 * i]);  // ticket 0 of every scheduler is granted up front
   }
   if (warp == A3_W_TMA) {
     tmem_alloc<512>(tmem_slot);
@@ -571,22 +587,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
   if (warp == A3_W_TMA) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t ring = 0;
-      uint32_t qcnt0 = 0, qcnt1 = 0, qcnt2 = 0;
+      uint32_t ring = 0;  // Q tiles are fetched by each stream's own issuer: this thread never waits for a stream
       for (int k = 0; k < rounds; ++k) {
         A3Item it;
         if (!a3_item(sc, k, seg_start, it)) continue;
-#pragma unroll
-        for (int s = 0; s < A3_STREAMS; ++s) {
-          if (s >= it.cnt) continue;
-          const uint32_t qc = s == 0 ? qcnt0 : (s == 1 ? qcnt1 : qcnt2);
-          mbar_wait(&q_empty[s], (qc & 1) ^ 1);
-          if (s == 0) ++qcnt0; else if (s == 1) ++qcnt1; else ++qcnt2;
-          mbar_arrive_expect_tx(&q_full[s], AF_QTILE_BYTES);
-          const int qr = static_cast<int>(it.row0) + s * AF_BQ;
-          tma_load_2d(sQ + s * AF_QTILE_BYTES, &tmQKV, &q_full[s], it.h * AF_HD, qr);
-          tma_load_2d(sQ + s * AF_QTILE_BYTES + AF_SUB_BYTES, &tmQKV, &q_full[s], it.h * AF_HD, qr + 64);
-        }
         const int kr0 = it.b * T + it.j_lo * AF_BK;
         for (int jj = 0; jj < it.n_ring; ++jj, ++ring) {
           const uint32_t st = ring % A3_STAGES, ph = (ring / A3_STAGES) & 1;
@@ -609,9 +613,24 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
       const uint64_t v_desc0 = make_smem_desc_sw128(smem_u32(sRing + AF_SUB_BYTES), AF_SUB_BYTES, 1024);
       const uint32_t tS = tmem_base + s * A3_TCOLS, tP = tS + 64, tO = tS + 96;
       uint32_t ring0 = 0;  // ring position of the item's first subtile (same sequence as the producer)
-      uint32_t items = 0;  // active items of this stream so far (q_full / o_free parity)
+      uint32_t items = 0;  // active items of this stream so far (q_full / q_empty / o_free parity)
       uint32_t cs = 0;     // S tiles issued so far (s_empty parity)
       uint32_t cp = 0;     // P·V issued so far (p_full parity)
+      // requests the Q tile of this stream's next active item after item k (the buffer must be free: q_empty)
+      auto request_next_q = [&](int k_from) {
+        for (int kn = k_from; kn < rounds; ++kn) {
+          A3Item nx;
+          if (!a3_item(sc, kn, seg_start, nx)) continue;
+          const int pos = a3_pos(nx, s);
+          if (pos < 0) continue;
+          mbar_arrive_expect_tx(&q_full[s], AF_QTILE_BYTES);
+          const int qr = static_cast<int>(nx.row0) + pos * AF_BQ;
+          tma_load_2d(sQ + s * AF_QTILE_BYTES, &tmQKV, &q_full[s], nx.h * AF_HD, qr);
+          tma_load_2d(sQ + s * AF_QTILE_BYTES + AF_SUB_BYTES, &tmQKV, &q_full[s], nx.h * AF_HD, qr + 64);
+          return;
+        }
+      };
+      request_next_q(0);
       auto issue_s = [&](uint32_t rpos) {
         const uint32_t st = rpos % A3_STAGES, ph = (rpos / A3_STAGES) & 1;
         mbar_wait(&kv_full[st], ph);
@@ -626,7 +645,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
       for (int k = 0; k < rounds; ++k) {
         A3Item it;
         if (!a3_item(sc, k, seg_start, it)) continue;
-        const int n = a3_n(it, s);
+        const int n = a3_n(it, a3_pos(it, s));
         if (n > 0) {
           mbar_wait(&q_full[s], items & 1);
           tc_fence_after();
@@ -634,7 +653,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
           for (int jj = 0; jj < n; ++jj) {
             // S of the NEXT subtile goes out as soon as the current one has been read, ahead of this subtile's P·V
             if (jj + 1 < n) issue_s(ring0 + jj + 1);
-            if (jj + 1 == n - 1 || n == 1) umma_commit(&q_empty[s]);  // every S MMA of this item has been issued
+            if (jj + 1 == n - 1) umma_commit(&q_empty[s]);  // every S MMA of this item has been issued (n >= 2)
             mbar_wait(&p_full[s], cp & 1);
             ++cp;
             if (jj == 0) mbar_wait(&o_free[s], (items & 1) ^ 1);  // the previous item's epilogue has read O
@@ -646,6 +665,12 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
               umma_ts(tO, tP + kk * 8, v_desc + kk * (2048 >> 4), idesc_o, (jj > 0 || kk > 0) ? 1u : 0u);
             umma_commit(&kv_empty[st]);  // this stream is done with the stage (its S MMA ran earlier, in order)
             umma_commit(&pv_done[s]);
+            if (jj == n - 2) {
+              // the item's last S was issued a whole subtile ago: its Q buffer is free (or about to be) — fetch the
+              // next item's Q tile now, under this item's last subtile and epilogue
+              mbar_wait(&q_empty[s], items & 1);
+              request_next_q(k + 1);
+            }
           }
           ++items;
         }
@@ -671,11 +696,12 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
     for (int k = 0; k < rounds; ++k) {
       A3Item it;
       if (!a3_item(sc, k, seg_start, it)) continue;
-      const int n = a3_n(it, s);
+      const int pos = a3_pos(it, s);
+      const int n = a3_n(it, pos);
       if (n == 0) continue;
-      const int qi = (it.t0 + s) * AF_BQ + r;  // position within the sequence
-      const bool row_ok = qi < T;              // ragged tail: T need not be a multiple of 128
-      const int64_t grow = it.row0 + s * AF_BQ + r;
+      const int qi = (it.t0 + pos) * AF_BQ + r;  // position within the sequence
+      const bool row_ok = qi < T;                // ragged tail: T need not be a multiple of 128
+      const int64_t grow = it.row0 + pos * AF_BQ + r;
       const int seg_lo = (seg_start && row_ok) ? __ldg(seg_start + grow) : 0;
       float m_run = -INFINITY, l_run = 0.f;
 
@@ -716,8 +742,19 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
           m_run = m_new;
           l_run *= alpha;
         }
-        const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
-        const float2 nm2 = make_float2(-m_use, -m_use);
+        float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
+        // MUFU lock.  The three warps of a scheduler (one per stream) share one 4-lane MUFU pipe; left alone they fall
+        // into lock-step — all three in their exp2 pass (each at a third of the rate), then all three in their
+        // MUFU-free phases (TMEM load, max, P store, barriers) with the pipe idle: measured 55 % MUFU utilisation.
+        // A FIFO ticket lock per scheduler makes the exp2 passes exclusive, which staggers the warps: one runs its
+        // pass at the full MUFU rate while the other two do their MUFU-free work.  ticket t waits for the t-th release
+        // on grant[t & 1] (two barriers, so that the at most two waiters never share one).
+        uint32_t tk = 0;
+        if (lane == 0) tk = atomicAdd(&ticket[quarter], 1u);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        mbar_wait(&grant[2 * quarter + (tk & 1)], (tk >> 1) & 1);
+        asm volatile("" : "+f"(neg_m));  // everything below depends on neg_m: no exp2 work is hoisted above the lock
+        const float2 nm2 = make_float2(neg_m, neg_m);
         float2 ps0 = make_float2(0.f, 0.f), ps1 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int c8 = 0; c8 < AF_BK / 8; ++c8) {
@@ -736,6 +773,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
 #pragma unroll
           for (int i = 0; i < 4; ++i) t[c8 * 4 + i] = pack_bf16x2(e[i].x, e[i].y);
         }
+        float psum = (ps0.x + ps0.y) + (ps1.x + ps1.y);
+        asm volatile("" : "+f"(psum));  // ... and the release below is ordered behind every exp2 (they all feed psum)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&grant[2 * quarter + ((tk + 1) & 1)]);
         // the previous P·V must be complete before its P is overwritten or O rescaled
         mbar_wait(&pv_done[s], (c & 1) ^ 1);
         tc_fence_after();
@@ -752,7 +793,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
         }
         tmem_st32(tP, *reinterpret_cast<const uint32_t(*)[32]>(&t[0]));
         tmem_st_wait();
-        l_run += (ps0.x + ps0.y) + (ps1.x + ps1.y);
+        l_run += psum;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);

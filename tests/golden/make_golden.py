@@ -375,9 +375,91 @@ def gen_variants_fixture():
         {k: v['state_keys'] for k, v in out['optim'].items()}, out['nadamw_factory_error'])
 
 
+MICRO = dict(vocab_size=64, d_model=64, n_layers=1, n_heads=1, seq_len=32, expand='8/3', mlp_class='glu',
+             tie_embeddings=False, model='transformer')
+
+
+def _markov_rows(n_rows, T, seed, symbols=16):
+  gen = torch.Generator().manual_seed(seed)
+  trans = torch.softmax(torch.randn(symbols, symbols, generator=gen) * 3, dim=-1)
+  rows = []
+  for _ in range(n_rows):
+    seq = [int(torch.randint(0, symbols, (1,), generator=gen))]
+    for _t in range(T):
+      seq.append(int(torch.multinomial(trans[seq[-1]], 1, generator=gen)))
+    rows.append(seq)
+  return torch.tensor(rows, dtype=torch.int64)
+
+
+def gen_resume_fixture():
+  """(1) A checkpoint WRITTEN BY THE REFERENCE: its TorchEngine trains a micro model for 3 optimizer steps on the CPU
+  and its own checkpoint_utils.save_checkpoint writes ckpt_step_3.pth (fused AdamW, so `step` is a tensor exactly as on
+  the GPU); the reference then keeps training and the next losses are recorded — SURVEY §8(f) N3 "cross-loading
+  reference checkpoints".  (2) The reference's loss curve with tie_embeddings=True (N4)."""
+  import shutil
+  import tempfile
+
+  from absl import flags
+
+  flags.DEFINE_integer('job_idx', None, 'stand-in for train.py:15 (utils.get_exp_dir_path reads it)')
+  flags.FLAGS(['make_golden'])
+  import checkpoint_utils
+  from engine import TorchEngine
+  from models import construct_model
+
+  T = MICRO['seq_len']
+  out = {'cfg': MICRO}
+  tmp = tempfile.mkdtemp()
+  cfgd = make_cfg(grad_accumulation_steps=1, fused_optim=True, steps_budget=12, out_dir=tmp, exp_name='golden',
+                  save_optim=True, save_scheduler=True, save_scaler=True)
+  Cfg = namedtuple('Cfg', cfgd.keys())
+  torch.manual_seed(31)
+  model, _ = construct_model(namedtuple('M', MICRO.keys())(**MICRO))
+  out['init_state_dict'] = {k: v.detach().clone() for k, v in model.state_dict().items()}
+  eng = TorchEngine(model, Cfg(**cfgd), 'cpu', None, None)
+  data = _markov_rows(8, T, seed=77)
+  losses = []
+  for i in range(3):
+    losses.append(float(eng.step({'input_ids': data[i : i + 1]})))
+  os.makedirs(os.path.join(tmp, 'golden'), exist_ok=True)
+  checkpoint_utils.save_checkpoint(3, model, eng, Cfg(**cfgd), {'train/loss': losses})
+  shutil.copy(os.path.join(tmp, 'golden', 'ckpt_step_3.pth'), os.path.join(HERE, 'ref_ckpt_step_3.pth'))
+  after = [float(eng.step({'input_ids': data[i : i + 1]})) for i in range(3, 8)]
+  # the reference resuming from its own file reproduces `after` (sanity of the fixture itself)
+  ck = torch.load(os.path.join(HERE, 'ref_ckpt_step_3.pth'), map_location='cpu')
+  model2, _ = construct_model(namedtuple('M', MICRO.keys())(**MICRO))
+  eng2 = TorchEngine(model2, Cfg(**dict(cfgd, resume=True)), 'cpu', None, ck)
+  again = [float(eng2.step({'input_ids': data[i : i + 1]})) for i in range(3, 8)]
+  assert max(abs(a - b) for a, b in zip(after, again)) < 1e-5, (after, again)
+  out['resume'] = {'engine_cfg': {k: v for k, v in cfgd.items() if k not in ('out_dir', 'exp_name')},
+                   'data': data.tolist(), 'losses_before': losses, 'losses_after': after,
+                   'optimizer_state_keys': sorted(ck['optimizer']['state'][0].keys()),
+                   'step_dtype': str(ck['optimizer']['state'][0]['step'].dtype),
+                   'ckpt_keys': sorted(ck.keys())}
+  shutil.rmtree(tmp)
+
+  tied_cfg = dict(MICRO, tie_embeddings=True)
+  torch.manual_seed(32)
+  modelt, _ = construct_model(namedtuple('M', tied_cfg.keys())(**tied_cfg))
+  assert modelt.lm_head.weight is modelt.embed_tokens.weight
+  cfgt = make_cfg(grad_accumulation_steps=2, steps_budget=8)
+  init_t = {k: v.detach().clone() for k, v in modelt.state_dict().items()}
+  engt = TorchEngine(modelt, namedtuple('Cfg', cfgt.keys())(**cfgt), 'cpu', None, None)
+  datat = _markov_rows(16, T, seed=78)
+  lt = [float(engt.step({'input_ids': datat[i : i + 1]})) for i in range(16)]
+  out['tied'] = {'cfg': tied_cfg, 'engine_cfg': cfgt, 'init_state_dict': init_t, 'data': datat.tolist(), 'losses': lt,
+                 'final_embed_norm': float(modelt.embed_tokens.weight.double().norm())}
+  torch.save(out, os.path.join(HERE, 'resume_tied.pt'))
+  print('resume', losses, after, '| tied', lt[0], '->', lt[-1], out['resume']['optimizer_state_keys'],
+        out['resume']['step_dtype'])
+
+
 if __name__ == '__main__':
   if len(sys.argv) > 1 and sys.argv[1] == 'variants':
     gen_variants_fixture()
+    sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == 'resume':
+    gen_resume_fixture()
     sys.exit(0)
   gen_model_fixture()
   gen_components_fixture()
@@ -387,3 +469,4 @@ if __name__ == '__main__':
   gen_misc_fixture()
   gen_init_fixture()
   gen_variants_fixture()
+  gen_resume_fixture()

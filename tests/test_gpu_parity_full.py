@@ -1,0 +1,271 @@
+"""GPU parity at the shapes and through the paths the small tests do not reach (VERDICT r1 "harden parity"):
+the 420M attention grid and GEMM shapes against fp64 / fp32 evaluations of the same bf16 operands on sampled rows,
+an engine loss curve whose attention and GEMMs are multi-tile, tied embeddings, a checkpoint written by the reference,
+and a real DataLoader (pinned memory + workers) driving the engine while CUDA graphs are being captured."""
+
+import os
+from collections import namedtuple
+
+import pytest
+import torch
+
+from conftest import assert_close, assert_close_elementwise
+from oracle import plainlm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+BF16_RTOL = 2e-2
+bf16 = torch.bfloat16
+
+
+def _cfg(**kw):
+  return namedtuple('Cfg', kw.keys())(**kw)
+
+
+def _engine_cfg(**over):
+  base = dict(seq_len=32, grad_accumulation_steps=1, grad_clip=1.0, dtype='bfloat16', intra_doc_masking=False,
+              resume=False, torch_compile=False, weight_decay=0.1, optim='adamw', lr=3e-3, beta1=0.9, beta2=0.95,
+              fused_optim=True, scheduler='warmup_cosine', warmup_steps=0.1, cooldown_steps=None, lr_start=0.0,
+              lr_end=1e-5, lr_end_pct=None, steps_budget=20, dampening=0.0)
+  base.update(over)
+  return base
+
+
+# ------------------------------------------------------------------------------------------- attention, 420M grid
+@pytest.mark.parametrize('doc', [False, True])
+def test_attention_420m_grid_sampled_fp64(doc):
+  """B=8, H=16, T=2048 (every CTA of the real launch): forward and backward against an fp64 evaluation of the same
+  bf16 q, k, v, dout on sampled (batch, head) pairs — all 2048 rows of each sampled pair."""
+  from plainlm_b200 import ops
+  from plainlm_b200.data_utils import seg_start_from_docs_lengths
+
+  B, T, H, hd = 8, 2048, 16, 64
+  d = H * hd
+  g = torch.Generator().manual_seed(420)
+  qkv = torch.randn(B * T, 3 * d, generator=g).to(bf16).to(DEV)
+  dout = (torch.randn(B * T, d, generator=g) * 0.5).to(bf16).to(DEV)
+  seg = None
+  if doc:
+    import random
+
+    rng = random.Random(3)
+    docs = []
+    for _ in range(B):
+      left, dl = T + 1, []
+      while left > 0:
+        n = min(left, max(1, int(rng.lognormvariate(6.0, 0.8))))
+        dl.append(n)
+        left -= n
+      docs.append(dl)
+    seg = seg_start_from_docs_lengths(docs, T).to(DEV)
+  out = torch.full((B * T, d), float('nan'), device=DEV, dtype=bf16)
+  lse = torch.empty(B, H, T, device=DEV)
+  segd = None if seg is None else seg.reshape(-1)
+  ops.attn_fwd(qkv, out, lse, B, T, H, hd, seg_start=segd)
+  dqkv = torch.full((B * T, 3 * d), float('nan'), device=DEV, dtype=bf16)
+  delta = torch.empty(B, H, T, device=DEV)
+  dq_acc = torch.empty(B * T, d, device=DEV)
+  ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd, seg_start=segd)
+  assert not torch.isnan(out.float()).any() and not torch.isnan(dqkv.float()).any()
+
+  v5 = qkv.view(B, T, 3, H, hd)
+  i = torch.arange(T, device=DEV)
+  for b, h in ((0, 0), (3, 7), (7, 15), (5, 2)):
+    q, k, v = (v5[b, :, j, h, :].double().clone().requires_grad_(True) for j in range(3))
+    s = (q @ k.t()) / 8.0
+    allowed = i[None, :] <= i[:, None]
+    if seg is not None:
+      allowed = allowed & (i[None, :] >= seg[b][:, None])
+    s = s.masked_fill(~allowed, float('-inf'))
+    p = torch.softmax(s, dim=-1)
+    o = p @ v
+    o.backward(dout.view(B, T, H, hd)[b, :, h, :].double())
+    what = f'b{b} h{h} doc{int(doc)}'
+    got_o = out.view(B, T, H, hd)[b, :, h, :]
+    assert_close(got_o, o, BF16_RTOL, what=what + ' out')
+    assert_close_elementwise(got_o, o, BF16_RTOL, what=what + ' out (elementwise)')
+    assert_close(lse[b, h], torch.logsumexp(s, dim=-1), 1e-3, what=what + ' lse')
+    g5 = dqkv.view(B, T, 3, H, hd)
+    for j, (name, ref) in enumerate((('dq', q.grad), ('dk', k.grad), ('dv', v.grad))):
+      assert_close(g5[b, :, j, h, :], ref, BF16_RTOL, what=f'{what} {name}')
+      assert_close_elementwise(g5[b, :, j, h, :], ref, BF16_RTOL, what=f'{what} {name} (elementwise)')
+
+
+# ------------------------------------------------------------------------------------------- GEMMs, 420M shapes
+def _sampled_rows_ref(a, b_nk, rows):
+  """fp32 contraction of the same bf16 operands for a sample of output rows: a [M, K], b_nk [N, K]."""
+  return a[rows].float() @ b_nk.float().t()
+
+
+def test_gemms_420m_shapes_sampled():
+  """Every GEMM shape of the 420M micro-step (M = 16384 tokens): forward with its fused epilogue, dgrad and wgrad,
+  against fp32 contractions of the same bf16 operands on 64 sampled output rows (all columns)."""
+  from plainlm_b200 import ops, _lib
+
+  M, d, F, T, hd = 16384, 1024, 2816, 2048, 64
+  g = torch.Generator().manual_seed(7)
+  rnd = lambda *s, sc=1.0: (torch.randn(*s, generator=g) * sc).to(bf16).to(DEV)  # noqa: E731
+  rows = torch.randint(0, M, (64,), generator=g).to(DEV)
+  x = rnd(M, d)
+  table = orc.rope_table(hd, T).to(DEV)
+  # qkv + RoPE epilogue
+  wqkv = rnd(3 * d, d, sc=0.05)
+  qkv = torch.empty(M, 3 * d, device=DEV, dtype=bf16)
+  ops.gemm(x, wqkv, qkv, epilogue=_lib.EPI_BF16_ROPE, rope_table=table, rope_cols=2 * d, rope_T=T, head_dim=hd)
+  ref = _sampled_rows_ref(x, wqkv, rows)
+  pos = (rows % T).cpu()
+  rot = orc.apply_rope(ref[:, : 2 * d].reshape(1, 64, 2 * d // hd, hd).transpose(0, 1).cpu(), table.cpu()[pos][:, None])
+  ref_r = torch.cat([rot.reshape(64, 2 * d).to(DEV), ref[:, 2 * d :]], dim=1)
+  assert_close(qkv[rows], ref_r, BF16_RTOL, what='qkv + rope')
+  assert_close_elementwise(qkv[rows], ref_r, BF16_RTOL, what='qkv + rope (elementwise)')
+  # out-proj and fc2 with the fp32 residual epilogue
+  res = torch.randn(M, d, generator=g).to(DEV)
+  for K, name in ((d, 'out-proj'), (F, 'fc2')):
+    a, w = rnd(M, K), rnd(d, K, sc=0.05)
+    y = torch.empty(M, d, device=DEV)
+    ops.gemm(a, w, y, epilogue=_lib.EPI_RESID_F32, residual=res)
+    assert_close_elementwise(y[rows], _sampled_rows_ref(a, w, rows) + res[rows], 1e-3, what=name + ' + residual')
+  # fc1 with the SwiGLU epilogue
+  w1 = rnd(2 * F, d, sc=0.05)
+  u = torch.empty(M, 2 * F, device=DEV, dtype=bf16)
+  h = torch.empty(M, F, device=DEV, dtype=bf16)
+  ops.gemm(x, w1, u, epilogue=_lib.EPI_BF16_SWIGLU, out2=h)
+  ref_u = _sampled_rows_ref(x, w1, rows)
+  assert_close_elementwise(u[rows], ref_u, BF16_RTOL, what='fc1 u')
+  ub = ref_u.to(bf16).float()
+  assert_close_elementwise(h[rows], torch.nn.functional.silu(ub[:, :F]) * ub[:, F:], BF16_RTOL, what='fc1 swiglu')
+  # dgrad (weights read in place as an MN-major operand) and wgrad (contraction over the 16384 tokens, fp32 accumulate)
+  dy = rnd(M, 2 * F, sc=0.1)
+  dx = torch.empty(M, d, device=DEV, dtype=bf16)
+  ops.gemm(dy, w1, dx, a_kmajor=True, b_kmajor=False)
+  assert_close_elementwise(dx[rows], dy[rows].float() @ w1.float(), BF16_RTOL, what='fc1 dgrad')
+  dw = torch.ones(2 * F, d, device=DEV)
+  ops.gemm(dy, x, dw, a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ATOMIC_F32, splits=0)
+  wrows = torch.randint(0, 2 * F, (64,), generator=g).to(DEV)
+  ref_dw = 1.0 + dy[:, wrows].float().t() @ x.float()
+  assert_close_elementwise(dw[wrows], ref_dw, 2e-3, what='fc1 wgrad (+= into fp32)')
+
+
+# ------------------------------------------------------------------------------------------- multi-tile loss curve
+def test_loss_curve_multitile_vs_oracle():
+  """d = 512, T = 512, 8 heads, 2 layers: attention runs 4 query tiles x up to 8 key subtiles per head, every GEMM
+  several K blocks and N tiles.  30 optimizer steps (accumulation 2) against the oracle's bf16 restatement on the CPU
+  with the same weights and tokens: every micro-step loss within 1 % (BASELINE.json north_star)."""
+  from plainlm_b200.engine import TorchEngine
+  from plainlm_b200.models import construct_model
+
+  mc = dict(vocab_size=1024, d_model=512, n_layers=2, n_heads=8, seq_len=512, expand='8/3', mlp_class='glu',
+            tie_embeddings=False, model='transformer')
+  cfgd = _engine_cfg(seq_len=512, grad_accumulation_steps=2, steps_budget=30, lr=1e-3)
+  model, _ = construct_model(_cfg(**mc))
+  params = orc.init_params(1024, 512, 2, 8, seed=21)
+  model.load_state_dict(params, strict=True)
+  eng = TorchEngine(model, _cfg(**cfgd), DEV, None, None)
+  tr = orc.OracleTrainer(params, dict(cfgd, n_heads=8), 'bf16')
+  g = torch.Generator().manual_seed(99)
+  trans = torch.softmax(torch.randn(64, 64, generator=g) * 3, dim=-1)
+  B, T = 2, 512
+  worst, first, last = 0.0, None, None
+  for _ in range(60):
+    seq = torch.empty(B, T + 1, dtype=torch.int64)
+    seq[:, 0] = torch.randint(0, 64, (B,), generator=g)
+    for t in range(T):
+      seq[:, t + 1] = torch.multinomial(trans[seq[:, t]], 1, generator=g).squeeze(1)
+    ref = float(tr.step({'input_ids': seq}))
+    got = eng.step({'input_ids': seq}).item()
+    worst = max(worst, abs(got - ref) / abs(ref))
+    first = got if first is None else first
+    last = got
+  assert worst <= 1e-2, worst
+  assert last < 0.8 * first
+
+
+# ------------------------------------------------------------------------------------------- reference fixtures
+@pytest.fixture(scope='module')
+def rt_fix(golden_dir):
+  return torch.load(os.path.join(golden_dir, 'resume_tied.pt'))
+
+
+def test_resume_from_reference_written_checkpoint(golden_dir, rt_fix):
+  """tests/golden/ref_ckpt_step_3.pth was written by the reference's own checkpoint_utils.save_checkpoint after its
+  TorchEngine trained 3 steps (fused AdamW: `step` tensors in the optimizer state).  TorchEngine(resume=True) must
+  load it and continue like the reference did (its recorded next losses; fp32 CPU vs bf16 here: 1 %)."""
+  from plainlm_b200.engine import TorchEngine
+  from plainlm_b200.models import construct_model
+
+  f = rt_fix['resume']
+  ckpt = torch.load(os.path.join(golden_dir, 'ref_ckpt_step_3.pth'), map_location='cpu')
+  assert sorted(ckpt.keys()) == f['ckpt_keys'] and ckpt['step'] == 3
+  torch.manual_seed(5)  # different init: everything must come from the checkpoint
+  model, _ = construct_model(_cfg(**rt_fix['cfg']))
+  cfgd = dict(f['engine_cfg'], dtype='bfloat16', resume=True)
+  eng = TorchEngine(model, _cfg(**cfgd), DEV, None, ckpt)
+  assert eng.micro_steps == 3
+  st0 = eng.optimizer.state_dict()['state'][0]
+  assert sorted(st0.keys()) == f['optimizer_state_keys'] and float(st0['step']) == 3.0
+  data = torch.tensor(f['data'])
+  got = [eng.step({'input_ids': data[i : i + 1]}).item() for i in range(3, 8)]
+  for a, b in zip(got, f['losses_after']):
+    assert abs(a - b) <= 1e-2 * abs(b), (got, f['losses_after'])
+  # and the state it writes back keeps the reference's layout
+  sd = eng.optimizer.state_dict()
+  assert sorted(sd['state'][0].keys()) == f['optimizer_state_keys'] and float(sd['state'][0]['step']) == 8.0
+
+
+def test_tied_embeddings_train_vs_reference(rt_fix):
+  """tie_embeddings=True (transformer.py:105-106,131-132): one storage, one gradient (embedding scatter + LM-head
+  wgrad accumulate into the same flat range).  16 micro-steps against the reference's recorded curve (1 %)."""
+  from plainlm_b200.engine import TorchEngine
+  from plainlm_b200.models import construct_model
+
+  f = rt_fix['tied']
+  model, _ = construct_model(_cfg(**f['cfg']))
+  assert model.lm_head.weight is model.embed_tokens.weight
+  model.load_state_dict(f['init_state_dict'], strict=True)
+  eng = TorchEngine(model, _cfg(**dict(f['engine_cfg'], dtype='bfloat16', fused_optim=True)), DEV, None, None)
+  data = torch.tensor(f['data'])
+  got = [eng.step({'input_ids': data[i : i + 1]}).item() for i in range(len(f['losses']))]
+  eng.check_nan(wait=True)
+  worst = max(abs(a - b) / abs(b) for a, b in zip(got, f['losses']))
+  assert worst <= 1e-2, (worst, got[-3:], f['losses'][-3:])
+  assert model.lm_head.weight.data_ptr() == model.embed_tokens.weight.data_ptr()
+  n = float(model.embed_tokens.weight.double().norm())
+  assert abs(n - f['final_embed_norm']) <= 2e-2 * f['final_embed_norm']
+
+
+# ------------------------------------------------------------------------------------------- real DataLoader
+class _Rows(torch.utils.data.Dataset):
+  def __init__(self, n, T, V):
+    self.data = torch.randint(0, V, (n, T + 1), generator=torch.Generator().manual_seed(3))
+
+  def __len__(self):
+    return self.data.shape[0]
+
+  def __getitem__(self, i):
+    return {'input_ids': self.data[i]}
+
+
+def test_engine_driven_by_pinned_dataloader_with_workers():
+  """The reference's loader runs with pin_memory=True and worker processes (data/dataloaders.py:52-66): its pin-memory
+  thread calls cudaHostAlloc while the engine captures its CUDA graphs during the first micro-steps.  The capture is
+  thread-local, so this must neither crash nor change results: same losses as feeding the same rows directly."""
+  from plainlm_b200.engine import TorchEngine
+  from plainlm_b200.models import construct_model
+
+  mc = dict(vocab_size=256, d_model=128, n_layers=2, n_heads=2, seq_len=64, expand='8/3', mlp_class='glu',
+            tie_embeddings=False, model='transformer')
+  ds = _Rows(48, 64, 256)
+  losses = []
+  for use_loader in (True, False):
+    model, _ = construct_model(_cfg(**mc))
+    model.load_state_dict(orc.init_params(256, 128, 2, 2, seed=4), strict=True)
+    eng = TorchEngine(model, _cfg(**_engine_cfg(seq_len=64, grad_accumulation_steps=2)), DEV, None, None)
+    if use_loader:
+      loader = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=False, num_workers=2, pin_memory=True,
+                                           prefetch_factor=2)
+      cur = [eng.step(batch).item() for batch in loader]
+    else:
+      cur = [eng.step({'input_ids': ds.data[i : i + 4]}).item() for i in range(0, 48, 4)]
+    eng.check_nan(wait=True)
+    losses.append(cur)
+  assert losses[0] == losses[1]

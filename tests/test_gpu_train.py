@@ -227,11 +227,46 @@ def test_nan_loss_raises():
 
   model, _ = _model()
   eng = TorchEngine(model, _cfg(**_engine_cfg(grad_accumulation_steps=1)), DEV, None, None)
+  eng.step({'input_ids': torch.zeros(1, 33, dtype=torch.int64)})  # a healthy step first
+  before = {k: v.detach().clone() for k, v in model.state_dict().items()}
+  m_before = eng.optimizer.state_dict()['state'][0]['exp_avg'].clone()
   with torch.no_grad():
-    model.lm_head.weight[0, 0] = float('nan')
-  eng.step({'input_ids': torch.zeros(1, 33, dtype=torch.int64)})
+    model.embed_tokens.weight[0, 0] = float('nan')  # token 0 is the whole batch below: every activation goes NaN
+  # reference: engine.py:116-117 raises BEFORE backward / optimizer.step; here the accumulation boundary checks every
+  # micro-step's loss before the update, so step() itself raises ...
   with pytest.raises(ValueError, match='Train loss is nan'):
-    eng.check_nan(wait=True)
+    eng.step({'input_ids': torch.zeros(1, 33, dtype=torch.int64)})
+  # ... and nothing was updated: weights (except the cell we poisoned), moments and bf16 shadows are untouched
+  after = model.state_dict()
+  for k, v in before.items():
+    if k == 'embed_tokens.weight':
+      assert torch.equal(after[k].flatten()[1:], v.flatten()[1:])
+    else:
+      assert torch.equal(after[k], v), k
+  assert torch.equal(eng.optimizer.state_dict()['state'][0]['exp_avg'], m_before)
+
+
+def test_nonfinite_gradients_never_reach_the_weights():
+  """Defence in depth: even if a caller swallowed the exception, the update kernels skip themselves when
+  the gradient norm they are handed is not finite."""
+  from plainlm_b200 import ops, _lib
+
+  n = 4096
+  p = torch.randn(n, device=DEV)
+  g = torch.randn(n, device=DEV)
+  g[7] = float('nan')
+  m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+  pb = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+  ws = torch.empty(_lib.SUMSQ_WORKSPACE, device=DEV)
+  gn = torch.zeros(1, device=DEV)
+  ops.sumsq(g, ws, gn)
+  assert not torch.isfinite(gn).item()
+  p0 = p.clone()
+  for max_norm in (1.0, 0.0):  # clipping on and off
+    ops.adamw_step(p, g, m, v, pb, 1e-3, 0.9, 0.95, 1e-8, 0.1, 1, gnorm_sq=gn, max_norm=max_norm)
+    ops.signsgd_step(p, g, m, pb, 1e-3, 0.9, 0.0, 0.1, True, gnorm_sq=gn, max_norm=max_norm)
+    ops.sgd_step(p, g, m, pb, 1e-3, 0.9, 0.0, 0.1, True, gnorm_sq=gn, max_norm=max_norm)
+  assert torch.equal(p, p0) and not m.any() and not v.any() and not pb.any()
 
 
 def test_eval_loop():
