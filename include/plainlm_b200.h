@@ -122,6 +122,12 @@ int plm_attn_bwd(const void* qkv, const void* out, const void* dout, const float
                  const float* rope_table, void* dqkv, float* delta, float* dq_acc, int32_t B, int32_t T, int32_t H,
                  int32_t hd, plm_stream_t stream);
 
+/* Diagnostics / A-B measurement only: the same backward with an explicit kernel variant (0 = plain, 1 = per-scheduler
+ * MUFU ticket lock in the compute warps; < 0 = the default plm_attn_bwd uses). */
+int plm_attn_bwd_variant(const void* qkv, const void* out, const void* dout, const float* lse,
+                         const int32_t* seg_start, const float* rope_table, void* dqkv, float* delta, float* dq_acc,
+                         int32_t B, int32_t T, int32_t H, int32_t hd, int32_t variant, plm_stream_t stream);
+
 /* Stand-alone RoPE on the q|k columns of a qkv buffer, in place (dir = +1 forward, -1 inverse). Used by tests and
  * by callers that bypass the fused GEMM epilogue. */
 int plm_rope_qk(void* qkv, const float* rope_table, int64_t rows, int32_t T, int32_t H, int32_t hd, int32_t dir,

@@ -42,6 +42,7 @@ SIGNATURES = {
   'plm_attn_fwd_variant': (c_int32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
   'plm_attn_fwd_v1': (c_int32, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
   'plm_attn_bwd': (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P]),
+  'plm_attn_bwd_variant': (c_int32, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P]),
   'plm_rope_qk': (c_int32, [_P, _P, _I64, _I32, _I32, _I32, _I32, _P]),
   'plm_rmsnorm_fwd': (c_int32, [_P, _P, _P, _P, _I64, _I32, _F, _P]),
   'plm_rmsnorm_bwd_blocks': (c_int32, [_I64]),

@@ -23,6 +23,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace plm {
@@ -156,6 +157,7 @@ __device__ __forceinline__ void store_bf16_row32(uint8_t* row_base, int r, int c
   }
 }
 
+template <bool LOCK>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQ,
@@ -184,6 +186,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* mma_done = s_full + 5;   // the dV, dK and dQ GEMMs of a step are complete (3 commits): P^T columns and the
                                      // dS^T buffer may be overwritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 6);
+  uint64_t* grant = s_full + 8;                                    // [4 schedulers][4]  MUFU lock (LOCK variant)
+  uint32_t* ticket = reinterpret_cast<uint32_t*>(s_full + 8 + 16);  // [4]
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // 128-byte-swizzle layout contract violated: fail the launch loudly
 
@@ -220,7 +224,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(sdp_free, AB_CWARPS);
     mbar_init(pds_ready, AB_CWARPS);
     mbar_init(mma_done, 3);
+    for (int g = 0; g < 16; ++g) mbar_init(&grant[g], 1);
+    for (int g = 0; g < 4; ++g) ticket[g] = 0;
     fence_barrier_init();
+    for (int g = 0; g < 4; ++g) mbar_arrive(&grant[4 * g]);  // ticket 0 of every scheduler is granted up front
   }
   if (warp == AB_W_MMA_S) {
     tmem_alloc<512>(tmem_slot);
@@ -421,10 +428,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       // P^T = exp2(S^T * scale*log2e - lse*log2e), masked;  dS^T = P^T o (dP^T - delta)  (softmax scale applied once,
       // in the dK / dQ epilogues)
       float p[32];
+      // MUFU lock (see attn_fwd.cu): the four compute warps of a scheduler share one 4-lane MUFU pipe and would
+      // otherwise run their exp2 bursts at the same time, then all sit in their MUFU-free phases (TMEM loads, dS math,
+      // stores, barriers) together.  A FIFO ticket lock per scheduler makes the bursts exclusive and staggers the warps.
+      // Ticket t waits for the t-th release on grant[t % 4] (four barriers: the <= 3 waiters never share one).
+      uint32_t tk = 0;
+      float sl2 = scale_log2;
+      if (LOCK) {
+        if (lane == 0) tk = atomicAdd(&ticket[quarter], 1u);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        mbar_wait(&grant[4 * quarter + (tk & 3)], (tk >> 2) & 1);
+        asm volatile("" : "+f"(sl2));  // the exp2 arguments depend on sl2: nothing of the burst is hoisted above the lock
+      }
       if (need_mask)
-        bwd_p_chunk<true>(ts, p, lse2, sg, kj, qpos0, scale_log2);
+        bwd_p_chunk<true>(ts, p, lse2, sg, kj, qpos0, sl2);
       else
-        bwd_p_chunk<false>(ts, p, lse2, sg, kj, qpos0, scale_log2);
+        bwd_p_chunk<false>(ts, p, lse2, sg, kj, qpos0, sl2);
+      if (LOCK) {
+        // The release must not overtake the exp2 burst: ptxas orders SASS by data dependence only, so the barrier address
+        // is made to depend on every exp2 result (xor of their bit patterns; the compared value never occurs: offset 0).
+        uint32_t x = 0;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) x ^= __float_as_uint(p[e]) ^ (__float_as_uint(p[e + 1]) << 1);
+        const uint32_t dep = (x == 0xffffffffu) ? 1u : 0u;  // p >= 0: bit 31 of x is never set
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&grant[4 * quarter + ((tk + 1) & 3)] + dep);
+      }
       uint32_t w[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(p[2 * e], p[2 * e + 1]);
@@ -523,10 +552,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
 }  // namespace plm
 
+#ifndef PLM_ATTN_BWD_DEFAULT_VARIANT
+#define PLM_ATTN_BWD_DEFAULT_VARIANT 0
+#endif
+
 extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
                             const int32_t* seg_start, const float* rope_table, void* dqkv, float* delta,
-                            float* dq_acc, int32_t B, int32_t T, int32_t H, int32_t hd, plm_stream_t stream_) {
+                            float* dq_acc, int32_t B, int32_t T, int32_t H, int32_t hd, plm_stream_t stream) {
+  return plm_attn_bwd_variant(qkv, out, dout, lse, seg_start, rope_table, dqkv, delta, dq_acc, B, T, H, hd, -1, stream);
+}
+
+// variant: 0 = plain, 1 = MUFU ticket lock in the compute warps; < 0 = library default.
+extern "C" int plm_attn_bwd_variant(const void* qkv, const void* out, const void* dout, const float* lse,
+                                    const int32_t* seg_start, const float* rope_table, void* dqkv, float* delta,
+                                    float* dq_acc, int32_t B, int32_t T, int32_t H, int32_t hd, int32_t variant,
+                                    plm_stream_t stream_) {
   using namespace plm;
+  if (variant < 0) {
+    // diagnostics: PLM_ATTN_BWD_VARIANT overrides the compiled default; read ONCE per process, never per launch
+    static std::once_flag vonce;
+    static int dflt = PLM_ATTN_BWD_DEFAULT_VARIANT;
+    std::call_once(vonce, [] {
+      const char* v = getenv("PLM_ATTN_BWD_VARIANT");
+      if (v && *v) dflt = atoi(v);
+    });
+    variant = dflt;
+  }
+  PLM_REQUIRE(variant == 0 || variant == 1, "attn_bwd: variant %d out of range", variant);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PLM_ENSURE_CONTEXT(qkv);
   PLM_REQUIRE(qkv && out && dout && lse && dqkv && delta && dq_acc, "attn_bwd: null pointer");
@@ -540,7 +592,9 @@ extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, 
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    attr_err = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
   });
   if (attr_err != cudaSuccess) return fail(PLM_ERR_CUDA, "attn_bwd smem attribute: %s", cudaGetErrorString(attr_err));
 
@@ -567,9 +621,14 @@ extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, 
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   dim3 grid((T + AB_T - 1) / AB_T, H, B);
-  attn_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, seg_start, rope_table,
-                                                         static_cast<__nv_bfloat16*>(dqkv), dq_acc, T, H, scale,
-                                                         scale * 1.4426950408889634f);
+  if (variant == 1)
+    attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, seg_start, rope_table,
+                                                                 static_cast<__nv_bfloat16*>(dqkv), dq_acc, T, H,
+                                                                 scale, scale * 1.4426950408889634f);
+  else
+    attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, seg_start, rope_table,
+                                                                  static_cast<__nv_bfloat16*>(dqkv), dq_acc, T, H,
+                                                                  scale, scale * 1.4426950408889634f);
   rc = check_launch("attn_bwd");
   if (rc != PLM_OK) return rc;
   {

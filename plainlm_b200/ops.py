@@ -84,12 +84,16 @@ def attn_fwd(qkv, out, lse, B, T, H, hd, seg_start=None, variant=None):
   return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd, seg_start=None, rope_table=None):
+def attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd, seg_start=None, rope_table=None, variant=None):
+  """variant (diagnostics): None = the library's default kernel, else plm_attn_bwd_variant."""
   lib = _lib.load()
-  check(lib.plm_attn_bwd(_ptr(qkv, bf16, 'qkv'), _ptr(out, bf16, 'out'), _ptr(dout, bf16, 'dout'),
-                         _ptr(lse, f32, 'lse'), _ptr(seg_start, torch.int32, 'seg_start'),
-                         _ptr(rope_table, f32, 'rope_table'), _ptr(dqkv, bf16, 'dqkv'), _ptr(delta, f32, 'delta'),
-                         _ptr(dq_acc, f32, 'dq_acc'), B, T, H, hd, _stream()), 'plm_attn_bwd')
+  args = (_ptr(qkv, bf16, 'qkv'), _ptr(out, bf16, 'out'), _ptr(dout, bf16, 'dout'), _ptr(lse, f32, 'lse'),
+          _ptr(seg_start, torch.int32, 'seg_start'), _ptr(rope_table, f32, 'rope_table'), _ptr(dqkv, bf16, 'dqkv'),
+          _ptr(delta, f32, 'delta'), _ptr(dq_acc, f32, 'dq_acc'), B, T, H, hd)
+  if variant is None:
+    check(lib.plm_attn_bwd(*args, _stream()), 'plm_attn_bwd')
+  else:
+    check(lib.plm_attn_bwd_variant(*args, int(variant), _stream()), 'plm_attn_bwd_variant')
   return dqkv
 
 

@@ -375,7 +375,7 @@ def gen_variants_fixture():
         {k: v['state_keys'] for k, v in out['optim'].items()}, out['nadamw_factory_error'])
 
 
-MICRO = dict(vocab_size=64, d_model=64, n_layers=1, n_heads=1, seq_len=32, expand='8/3', mlp_class='glu',
+MICRO = dict(vocab_size=64, d_model=128, n_layers=1, n_heads=2, seq_len=32, expand='1', mlp_class='glu',
              tie_embeddings=False, model='transformer')
 
 

@@ -113,9 +113,11 @@ def test_gemms_420m_shapes_sampled():
   qkv = torch.empty(M, 3 * d, device=DEV, dtype=bf16)
   ops.gemm(x, wqkv, qkv, epilogue=_lib.EPI_BF16_ROPE, rope_table=table, rope_cols=2 * d, rope_T=T, head_dim=hd)
   ref = _sampled_rows_ref(x, wqkv, rows)
-  pos = (rows % T).cpu()
-  rot = orc.apply_rope(ref[:, : 2 * d].reshape(1, 64, 2 * d // hd, hd).transpose(0, 1).cpu(), table.cpu()[pos][:, None])
-  ref_r = torch.cat([rot.reshape(64, 2 * d).to(DEV), ref[:, 2 * d :]], dim=1)
+  cs = table[rows % T]  # [64, hd/2, 2] (cos, sin) of each sampled row's position (models/embeddings.py:8-12)
+  xr = ref[:, : 2 * d].reshape(64, 2 * d // hd, hd // 2, 2)
+  cos, sin = cs[:, None, :, 0], cs[:, None, :, 1]
+  rot = torch.stack([xr[..., 0] * cos - xr[..., 1] * sin, xr[..., 1] * cos + xr[..., 0] * sin], dim=-1)
+  ref_r = torch.cat([rot.reshape(64, 2 * d), ref[:, 2 * d :]], dim=1)
   assert_close(qkv[rows], ref_r, BF16_RTOL, what='qkv + rope')
   assert_close_elementwise(qkv[rows], ref_r, BF16_RTOL, what='qkv + rope (elementwise)')
   # out-proj and fc2 with the fp32 residual epilogue
@@ -268,4 +270,7 @@ def test_engine_driven_by_pinned_dataloader_with_workers():
       cur = [eng.step({'input_ids': ds.data[i : i + 4]}).item() for i in range(0, 48, 4)]
     eng.check_nan(wait=True)
     losses.append(cur)
-  assert losses[0] == losses[1]
+  # same rows, same weights: equal up to the order of the fp32 reduce-adds (wgrad split-K, dQ), which is not fixed
+  assert len(losses[0]) == len(losses[1]) == 12
+  for a, b in zip(*losses):
+    assert abs(a - b) <= 1e-4 * abs(b), losses

@@ -180,7 +180,7 @@ def case_attn_fwd(B, T, H, doc=False, variant=None, scale=1.0):
   return r
 
 
-def case_attn_bwd(B, T, H, doc=False, rope=False):
+def case_attn_bwd(B, T, H, doc=False, rope=False, variant=None):
   import torch
   from plainlm_b200 import ops
 
@@ -204,9 +204,9 @@ def case_attn_bwd(B, T, H, doc=False, rope=False):
   dqkv = torch.full((B * T, 3 * d), float('nan'), device=dev, dtype=torch.bfloat16)
   delta = torch.empty(B, H, T, device=dev)
   dq_acc = torch.empty(B * T, d, device=dev)
-  ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd, seg_start=seg, rope_table=tab)
+  ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd, seg_start=seg, rope_table=tab, variant=variant)
   torch.cuda.synchronize()
-  name = f'attn_bwd B{B} T{T} H{H} doc{int(doc)} rope{int(rope)}'
+  name = f'attn_bwd B{B} T{T} H{H} doc{int(doc)} rope{int(rope)} variant {variant}'
   r = _err(name, dqkv, dqkv_ref)
   for nm, sl in (('dq', slice(0, d)), ('dk', slice(d, 2 * d)), ('dv', slice(2 * d, 3 * d))):
     e = _err(nm, dqkv[:, sl], dqkv_ref[:, sl])
@@ -622,6 +622,8 @@ def case_attn_perf():
     ('attn_fwd variant 11', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant=11), flops_fwd),
     ('attn_fwd variant 12', lambda: ops.attn_fwd(qkv, out, lse, B, T, H, hd, variant=12), flops_fwd),
     ('attn_bwd', lambda: ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd), 2.5 * flops_fwd),
+    ('attn_bwd variant 0', lambda: ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd, variant=0), 2.5 * flops_fwd),
+    ('attn_bwd variant 1', lambda: ops.attn_bwd(qkv, out, dout, lse, dqkv, delta, dq_acc, B, T, H, hd, variant=1), 2.5 * flops_fwd),
   ):
     for _ in range(3):
       fn()
@@ -693,6 +695,9 @@ CASES['attn_bwd_1tile'] = lambda: case_attn_bwd(1, 128, 1)
 CASES['attn_bwd_2tile'] = lambda: case_attn_bwd(1, 256, 1)
 CASES['attn_bwd_multi'] = lambda: case_attn_bwd(2, 512, 3)
 CASES['attn_bwd_doc_rope'] = lambda: case_attn_bwd(2, 512, 2, doc=True, rope=True)
+CASES['attn_bwd_multi_lock'] = lambda: case_attn_bwd(2, 512, 3, variant=1)
+CASES['attn_bwd_doc_rope_lock'] = lambda: case_attn_bwd(2, 512, 2, doc=True, rope=True, variant=1)
+CASES['attn_bwd_long_lock'] = lambda: case_attn_bwd(1, 2048, 2, variant=1)
 CASES['bandwidth'] = case_bandwidth
 CASES['gemm_perf'] = case_gemm_perf
 CASES['attn_perf'] = case_attn_perf
