@@ -307,6 +307,12 @@ def run_ours(args):
   value = tokens_per_step * K / (ms_value / 1e3)
   e2e_value = tokens_per_step * K / (ms_e2e / 1e3)
   ppt = doc_pairs_per_token(docs, T) if docs else None  # document masking: count only the allowed (query, key) pairs
+  # document masking sends only the lengths (int32) and B + 1 offsets per micro-batch; the segment map is built on device
+  doc_h2d_bytes = 0
+  if my_docs:
+    n_micro_timed = K * accum
+    used = my_docs[W * accum * B : (W + K) * accum * B]
+    doc_h2d_bytes = (4 * sum(len(dl) for dl in used) + 4 * (B + 1) * n_micro_timed) / K
   ftok = flops_per_token(c, ppt)
   peaks = load_peaks()
 
@@ -376,7 +382,7 @@ def run_ours(args):
               'vs_nominal_2250': round(value * ftok / world / 2250e12, 4),
               'vs_measured_sustained': round(value * ftok / world / (peaks['tf_sustained'] * 1e12), 4)},
       'e2e': {'value': round(e2e_value, 1), 'unit': 'tokens/s', 'ms_per_step': round(ms_e2e / K, 3),
-              'h2d_bytes_per_step': int(2 * B * T * 8 * accum + (B * T * 4 * accum if c['intra_doc_masking'] else 0)),
+              'h2d_bytes_per_step': int(2 * B * T * 8 * accum + doc_h2d_bytes),
               'd2h_bytes_per_step': int(4 * accum + 4)},
       'gpu_launches': int(launches),
       'clocks': clocks,

@@ -122,8 +122,8 @@ int plm_attn_bwd(const void* qkv, const void* out, const void* dout, const float
                  const float* rope_table, void* dqkv, float* delta, float* dq_acc, int32_t B, int32_t T, int32_t H,
                  int32_t hd, plm_stream_t stream);
 
-/* Diagnostics / A-B measurement only: the same backward with an explicit kernel variant (0 = plain, 1 = per-scheduler
- * MUFU ticket lock in the compute warps; < 0 = the default plm_attn_bwd uses). */
+/* Diagnostics / A-B measurement only: the same backward with an explicit kernel variant (0 = one CTA per (key tile, head,
+ * batch), 1 = persistent CTAs; < 0 = the default plm_attn_bwd uses). */
 int plm_attn_bwd_variant(const void* qkv, const void* out, const void* dout, const float* lse,
                          const int32_t* seg_start, const float* rope_table, void* dqkv, float* delta, float* dq_acc,
                          int32_t B, int32_t T, int32_t H, int32_t hd, int32_t variant, plm_stream_t stream);

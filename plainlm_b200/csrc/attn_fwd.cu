@@ -474,8 +474,8 @@ constexpr int A3_W_TMA = A3_W_ISSUE + A3_STREAMS;  // warp 15
 constexpr int A3_THREADS = (A3_W_TMA + 1) * 32;
 constexpr int A3_OFF_RING = A3_STREAMS * AF_QTILE_BYTES;
 constexpr int A3_OFF_BARS = A3_OFF_RING + A3_STAGES * AF_STAGE_BYTES;
-constexpr int A3_NBARS = 2 * A3_STAGES + 7 * A3_STREAMS + 8;  // + 2 grant barriers per scheduler (MUFU lock)
-constexpr int A3_SMEM = A3_OFF_BARS + A3_NBARS * 8 + 16 + 16;  // + tmem slot + 4 ticket counters
+constexpr int A3_NBARS = 2 * A3_STAGES + 7 * A3_STREAMS;
+constexpr int A3_SMEM = A3_OFF_BARS + A3_NBARS * 8 + 16;
 constexpr int A3_TCOLS = 160;  // TMEM columns per stream: S at +0, P at +64, O at +96
 
 struct A3Item {
@@ -538,9 +538,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
   uint64_t* p_full = q_full + 4 * A3_STREAMS;      //      P of the subtile is in tensor memory (4 warps)
   uint64_t* pv_done = q_full + 5 * A3_STREAMS;     //      the subtile's P·V has completed: P may be overwritten, O read
   uint64_t* o_free = q_full + 6 * A3_STREAMS;      //      the epilogue has read O (4 warps)
-  uint64_t* grant = q_full + 7 * A3_STREAMS;       // [4 schedulers][2]  MUFU lock, see softmax warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + A3_NBARS);
-  uint32_t* ticket = tmem_slot + 1;                // [4]
 
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
@@ -570,10 +568,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
       mbar_init(&pv_done[i], 1);
       mbar_init(&o_free[i], 4);
     }
-    for (int i = 0; i < 8; ++i) mbar_init(&grant[i], 1);
-    for (int i = 0; i < 4; ++i) ticket[i] = 0;
     fence_barrier_init();
-    for (int i = 0; i < 4; ++i) mbar_arrive(&grant[2 * i]);  // ticket 0 of every scheduler is granted up front
   }
   if (warp == A3_W_TMA) {
     tmem_alloc<512>(tmem_slot);
@@ -742,18 +737,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
           m_run = m_new;
           l_run *= alpha;
         }
-        float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
-        // MUFU lock.  The three warps of a scheduler (one per stream) share one 4-lane MUFU pipe; left alone they fall
-        // into lock-step — all three in their exp2 pass (each at a third of the rate), then all three in their
-        // MUFU-free phases (TMEM load, max, P store, barriers) with the pipe idle: measured 55 % MUFU utilisation.
-        // A FIFO ticket lock per scheduler makes the exp2 passes exclusive, which staggers the warps: one runs its
-        // pass at the full MUFU rate while the other two do their MUFU-free work.  ticket t waits for the t-th release
-        // on grant[t & 1] (two barriers, so that the at most two waiters never share one).
-        uint32_t tk = 0;
-        if (lane == 0) tk = atomicAdd(&ticket[quarter], 1u);
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-        mbar_wait(&grant[2 * quarter + (tk & 1)], (tk >> 1) & 1);
-        asm volatile("" : "+f"(neg_m));  // everything below depends on neg_m: no exp2 work is hoisted above the lock
+        const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
+        // (A per-scheduler FIFO lock that made the exp2 passes of the three warps sharing a MUFU pipe exclusive was
+        // measured and removed: 0.119 -> 0.137 ms.  The warps interleave on the pipe better than a lock hand-off, whose
+        // ~200-cycle wake-up leaves the pipe idle three times per round.)
         const float2 nm2 = make_float2(neg_m, neg_m);
         float2 ps0 = make_float2(0.f, 0.f), ps1 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -774,12 +761,6 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQKV, const int32_t* __res
           for (int i = 0; i < 4; ++i) t[c8 * 4 + i] = pack_bf16x2(e[i].x, e[i].y);
         }
         const float psum = (ps0.x + ps0.y) + (ps1.x + ps1.y);
-        // The release must not overtake the exp2 burst.  ptxas schedules SASS by data dependence only (an empty asm
-        // barrier is invisible to it: it moved the arrive up to the tenth MUFU), so the barrier ADDRESS is made to
-        // depend on psum, which every exp2 of the pass feeds.  The NaN payload below never occurs: the offset is 0.
-        const uint32_t dep = (__float_as_uint(psum) == 0x7fc5a5a5u) ? 1u : 0u;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&grant[2 * quarter + ((tk + 1) & 1)] + dep);
         // the previous P·V must be complete before its P is overwritten or O rescaled
         mbar_wait(&pv_done[s], (c & 1) ^ 1);
         tc_fence_after();

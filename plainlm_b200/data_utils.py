@@ -31,3 +31,17 @@ def rank_partition(n_rows, world, rank):
   """Rows seen by `rank`: DistributedSampler(shuffle=False, drop_last=True) as built at data/dataloaders.py:91."""
   per = n_rows // world
   return list(range(rank, per * world, world))
+
+
+def pack_docs_lengths(docs_lengths, seq_len):
+  """Flattens `docs_lengths` for the on-device segment-map kernel (plm_seg_start_from_lengths): returns
+  (lengths int32 [n_docs_total], offsets int32 [B + 1]).  Keeps the reference's validation
+  (data/datasets/data_prep_utils.py:10-11: every row's lengths must sum to seq_len + 1)."""
+  flat, offsets = [], [0]
+  for lengths in docs_lengths:
+    row = [int(n) for n in lengths]
+    if sum(row) != seq_len + 1:
+      raise ValueError('Sum of doc_boundaries does not match max_seq_length.')
+    flat.extend(row)
+    offsets.append(len(flat))
+  return torch.tensor(flat, dtype=torch.int32), torch.tensor(offsets, dtype=torch.int32)

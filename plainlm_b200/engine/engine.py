@@ -20,7 +20,8 @@ What changes underneath (SURVEY.md §3.2 -> here):
 import torch
 from torch import distributed as dist
 
-from ..data_utils import seg_start_from_docs_lengths
+from .. import ops
+from ..data_utils import pack_docs_lengths
 from ..dp import GradReducer, broadcast_parameters
 from ..models import get_param_groups
 from ..optim import intialize_optimizer, initialize_scheduler
@@ -54,6 +55,26 @@ class _HostStaging:
     ev.record()
     rec[2] = ev
     return dev
+
+  def put_prefix(self, name, cpu_tensor, capacity):
+    """Like put() for a 1-D tensor whose length varies from step to step: one pinned / device pair of `capacity`
+    elements per slot, only the used prefix is copied."""
+    key = (name, self.k, capacity, cpu_tensor.dtype)
+    rec = self.bufs.get(key)
+    if rec is None:
+      rec = [torch.empty(capacity, dtype=cpu_tensor.dtype, pin_memory=True),
+             torch.empty(capacity, dtype=cpu_tensor.dtype, device=self.device), None]
+      self.bufs[key] = rec
+    pinned, dev, ev = rec
+    if ev is not None:
+      ev.synchronize()
+    n = cpu_tensor.numel()
+    pinned[:n].copy_(cpu_tensor)
+    dev[:n].copy_(pinned[:n], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    rec[2] = ev
+    return dev[:n]
 
   def advance(self):
     self.k = (self.k + 1) % self.slots
@@ -106,6 +127,7 @@ class TorchEngine(torch.nn.Module):
 
     dev = self.rt.flat.params.device
     self._staging = _HostStaging(dev)
+    self._seg_ring = {}
     self._sumsq_ws = sumsq_workspace(dev)
     self._gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
     n_slots = max(int(self.accumulation_steps), 1)  # one pinned slot per micro-step of an accumulation cycle
@@ -114,22 +136,37 @@ class TorchEngine(torch.nn.Module):
 
   # ------------------------------------------------------------------------------------------ batch staging
   def _move_to_device(self, batch):
-    """reference: engine.py:13-34.  Slicing is done on the host (bit-exact integers), the dense mask is replaced by
-    int32 segment starts built from `docs_lengths`."""
+    """reference: engine.py:13-34.  Slicing is done on the host (bit-exact integers).  The dense (B, T, T) mask the
+    reference builds on the device with a Python loop per document (engine.py:19-23) is replaced by int32 segment
+    starts: only the document lengths cross PCIe (a few hundred bytes) and plm_seg_start_from_lengths expands them on
+    the device into seg_start[B*T]."""
     ids = batch['input_ids']
     T = self.seq_len
+    B = ids.shape[0]
     seg = None
     if ids.is_cuda:
       inputs, targets = ids[:, :T].contiguous(), ids[:, 1 : T + 1].contiguous()
-      if self.intra_doc_masking:
-        seg = seg_start_from_docs_lengths(batch['docs_lengths'], T).to(ids.device).reshape(-1)
-      return inputs, targets, seg
-    inputs = self._staging.put('inputs', ids[:, :T])
-    targets = self._staging.put('targets', ids[:, 1 : T + 1])
+    else:
+      inputs = self._staging.put('inputs', ids[:, :T])
+      targets = self._staging.put('targets', ids[:, 1 : T + 1])
     if self.intra_doc_masking:
-      seg = self._staging.put('seg', seg_start_from_docs_lengths(batch['docs_lengths'], T)).reshape(-1)
+      lengths, offsets = pack_docs_lengths(batch['docs_lengths'], T)
+      d_len = self._staging.put_prefix('doc_lengths', lengths, B * (T + 1))
+      d_off = self._staging.put_prefix('doc_offsets', offsets, B + 1)
+      seg = self._seg_buf(B, T)
+      ops.seg_start_from_lengths(d_len, d_off, seg, B, T)
     self._staging.advance()
     return inputs, targets, seg
+
+  def _seg_buf(self, B, T):
+    """Segment maps live in a small ring of device buffers (a micro-step's map must outlive the next staging)."""
+    key = (B, T)
+    ring = self._seg_ring.get(key)
+    if ring is None:
+      ring = [[torch.empty(B * T, dtype=torch.int32, device=self.rt.flat.params.device) for _ in range(3)], 0]
+      self._seg_ring[key] = ring
+    ring[1] = (ring[1] + 1) % 3
+    return ring[0][ring[1]]
 
   # ------------------------------------------------------------------------------------------ NaN guard
   def _record_loss(self, loss, k):

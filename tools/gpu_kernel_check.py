@@ -695,9 +695,12 @@ CASES['attn_bwd_1tile'] = lambda: case_attn_bwd(1, 128, 1)
 CASES['attn_bwd_2tile'] = lambda: case_attn_bwd(1, 256, 1)
 CASES['attn_bwd_multi'] = lambda: case_attn_bwd(2, 512, 3)
 CASES['attn_bwd_doc_rope'] = lambda: case_attn_bwd(2, 512, 2, doc=True, rope=True)
-CASES['attn_bwd_multi_lock'] = lambda: case_attn_bwd(2, 512, 3, variant=1)
-CASES['attn_bwd_doc_rope_lock'] = lambda: case_attn_bwd(2, 512, 2, doc=True, rope=True, variant=1)
-CASES['attn_bwd_long_lock'] = lambda: case_attn_bwd(1, 2048, 2, variant=1)
+CASES['attn_bwd_multi_persist'] = lambda: case_attn_bwd(2, 512, 3, variant=1)
+CASES['attn_bwd_doc_rope_persist'] = lambda: case_attn_bwd(2, 512, 2, doc=True, rope=True, variant=1)
+CASES['attn_bwd_long_persist'] = lambda: case_attn_bwd(1, 2048, 2, variant=1)
+CASES['attn_bwd_1tile_persist'] = lambda: case_attn_bwd(1, 128, 1, variant=1)
+CASES['attn_bwd_ragged_persist'] = lambda: case_attn_bwd(2, 200, 2, variant=1)
+CASES['attn_bwd_many_items_persist'] = lambda: case_attn_bwd(3, 1024, 40, doc=True, rope=True, variant=1)
 CASES['bandwidth'] = case_bandwidth
 CASES['gemm_perf'] = case_gemm_perf
 CASES['attn_perf'] = case_attn_perf
