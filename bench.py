@@ -255,9 +255,13 @@ def run_ours(args):
     return t.item()
 
   # ---------------------------------------------------------------- region 1: device-resident inputs (`value`)
+  DP_CHECK_STEPS = 2  # optimizer steps after which the data-parallel state is snapshotted for the equivalence check
+  dp_snap = None
   for s in range(W):
     for m in range(accum):
       dev_step(s * accum + m)
+    if world > 1 and rank == 0 and s + 1 == DP_CHECK_STEPS:
+      dp_snap = engine.rt.flat.params.clone()
   barrier()
   sampler = ClockSampler(local_rank)
   if rank == 0:
@@ -302,6 +306,45 @@ def run_ours(args):
   summ = prof.summary()
   ops.set_profiler(None)
   os.environ.pop('PLM_NO_SIDE_STREAM', None)
+
+  # ---------------------------------------------------------------- data-parallel equivalence (N > 1)
+  # (1) every replica holds bit-identical weights after the run; (2) N ranks x accum micro-batches == ONE rank running
+  # N x accum micro-batches on the same rows (reference: DDP averages the per-rank gradients, engine.py:64-65,104-105).
+  dp_equiv = None
+  if world > 1:
+    flat = engine.rt.flat.params
+    chk = flat.view(torch.int32).to(torch.int64).sum().reshape(1)
+    allchk = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allchk, chk)
+    identical = all(int(c) == int(allchk[0]) for c in allchk)
+    if rank == 0:
+      _, _, tdict1 = make_cfgs(c, 2 * (K + W) + 4)
+      cfg1 = dict(tdict1, grad_accumulation_steps=accum * world, data_parallel=False, cuda_graphs=True)
+      torch.manual_seed(100)
+      model1, _ = construct_model(mcfg)
+      eng1 = TorchEngine(model1, namedtuple('Cfg', cfg1.keys())(**cfg1), device, None, None)
+      init1 = eng1.rt.flat.params.clone()
+      for s in range(DP_CHECK_STEPS):
+        for m in range(accum):
+          i = s * accum + m  # global micro-step i: rank r consumed rows {(i B + b) W + r}
+          for r in range(world):
+            blk = rows[[(i * B + b) * world + r for b in range(B)]]
+            seg1 = None
+            if docs:
+              seg1 = seg_start_from_docs_lengths([docs[(i * B + b) * world + r] for b in range(B)], T).to(device).reshape(-1)
+            eng1.step_device(blk[:, :T].contiguous().to(device), blk[:, 1 : T + 1].contiguous().to(device), seg1)
+      torch.cuda.synchronize()
+      upd = (eng1.rt.flat.params - init1).double().norm().item()
+      diff = (eng1.rt.flat.params - dp_snap).double().norm().item()
+      dp_equiv = {'replicas_bit_identical': identical, 'optimizer_steps': DP_CHECK_STEPS,
+                  'diff_over_update_norm': round(diff / max(upd, 1e-30), 5),
+                  'what': f'{world} ranks x {accum} micro-batches vs 1 rank x {accum * world} micro-batches, same rows and init; '
+                          'bf16 gradient wire (pre-scaled 1/world): tolerance 0.15 of the update norm'}
+      del eng1, model1, init1, dp_snap
+      torch.cuda.empty_cache()
+      assert identical, 'data-parallel replicas diverged'
+      assert dp_equiv['diff_over_update_norm'] <= 0.15, dp_equiv
+    dist.barrier()
 
   tokens_per_step = B * T * accum * world
   value = tokens_per_step * K / (ms_value / 1e3)
@@ -393,6 +436,8 @@ def run_ours(args):
       out['cpu_baseline'] = cpu
     if gpu_ref is not None:
       out['gpu_eager_reference'] = gpu_ref
+    if dp_equiv is not None:
+      out['dp_equiv'] = dp_equiv
     print(json.dumps(out))
   if world > 1:
     dist.barrier()

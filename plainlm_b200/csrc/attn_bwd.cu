@@ -39,6 +39,16 @@ constexpr int AB_W_DRAIN = AB_CWARPS + 4;   // four dQ drain warps, one per TMEM
 constexpr int AB_THREADS = (AB_CWARPS + 8) * 32;
 constexpr int AB_REGS_COMPUTE = 96;  // setmaxnreg: compute warpgroups take registers from the auxiliary ones
 constexpr int AB_REGS_AUX = 48;
+// persistent kernel: a fourth issuer (dQ) and three padding warps make 28 warps = 7 warpgroups (setmaxnreg is per
+// warpgroup): 896 threads x 72 registers at launch = 64512 = 512 x 96 (compute) + 384 x 40 (everything else)
+constexpr int ABP_W_MMA_S = AB_CWARPS;
+constexpr int ABP_W_MMA_DV = AB_CWARPS + 1;
+constexpr int ABP_W_MMA_DK = AB_CWARPS + 2;
+constexpr int ABP_W_TMA = AB_CWARPS + 3;
+constexpr int ABP_W_DRAIN = AB_CWARPS + 4;   // 20..23
+constexpr int ABP_W_MMA_DQ = AB_CWARPS + 8;  // 24 (25..27 pad the warpgroup)
+constexpr int ABP_THREADS = (AB_CWARPS + 12) * 32;
+constexpr int ABP_REGS_AUX = 40;
 constexpr int AB_STAGES = 3;       // Q_i / dO_i ring
 constexpr int AB_TILE = AB_T * AB_HD * 2;  // 16 KB
 // K, V, (Q,dO) x AB_STAGES, dS^T (2 blocks), dQ staging (fp32 128 x 64), vectors (lse2, delta, seg) x stages, barriers
@@ -531,7 +541,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 // (key tile, head, batch) items in snake order over the heaviest-first list; tensor memory, barriers and the Q/dO ring
 // live across items (all parities run on global step counters), the producer prefetches the next item's Q/dO tiles
 // while the current one drains, and the dK/dV epilogue of item n overlaps the K/V fetch of item n+1.
-__global__ void __launch_bounds__(AB_THREADS, 1)
+__global__ void __launch_bounds__(ABP_THREADS, 1)
 attn_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const __grid_constant__ CUtensorMap tmDQ,
                 const float* __restrict__ lse, const float* __restrict__ delta, const int32_t* __restrict__ seg_start,
@@ -610,11 +620,11 @@ attn_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
     mbar_init(sdp_free, AB_CWARPS);
     mbar_init(pds_ready, AB_CWARPS);
     mbar_init(mma_done, 3);
-    mbar_init(kv_empty, 1);
+    mbar_init(kv_empty, 2);  // the S^T/dP^T issuer and the dQ issuer
     mbar_init(acc_free, AB_CWARPS);
     fence_barrier_init();
   }
-  if (warp == AB_W_MMA_S) {
+  if (warp == ABP_W_MMA_S) {
     tmem_alloc<512>(tmem_slot);
     tmem_relinquish();
   }
@@ -628,8 +638,8 @@ attn_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
   const uint32_t tS = tmem_base, tDP = tmem_base + 128, tDV = tmem_base + 256, tDK = tmem_base + 320,
                  tDQ = tmem_base + 384, tP = tmem_base + 448;
 
-  if (warp == AB_W_TMA) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AB_REGS_AUX));
+  if (warp == ABP_W_TMA) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ABP_REGS_AUX));
     // ------------------------------------------------------------ producer warp: lane 0 drives the Q_i, dO_i ring (K, V
     // are fetched by the S^T issuer, which alone knows when they are free), all 32 lanes stage the per-query vectors (lse*log2e, delta, seg_start) of the step next to its tiles.
     uint32_t g = 0;      // global step counter (ring slot and parities run across items)
@@ -658,68 +668,50 @@ attn_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         mbar_arrive(&qdo_full[st]);  // release: the vectors are visible to whoever acquires the barrier
       }
     }
-  } else if (warp == AB_W_MMA_S) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AB_REGS_AUX));
-    // ------------------------------------------------------------ MMA issuer 1: S^T = K Q^T, dP^T = V dO^T, dQ = dS K.
+  } else if (warp == ABP_W_MMA_S) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ABP_REGS_AUX));
+    // ------------------------------------------------------------ MMA issuer 1: S^T = K Q^T, dP^T = V dO^T.
     // S^T / dP^T of step g+1 only wait for step g's tiles to be READ out of tensor memory (sdp_free, early in the
-    // step); dQ of step g waits for its dS^T (pds_ready, late in the step) and for the previous dQ to have left tensor
-    // memory (dq_empty).
+    // step).  (In the non-persistent kernel this thread also issues dQ; a tcgen05.mma costs its issuer ~90 cycles, and
+    // with 16 per step the next step's scores arrived ~650 cycles after the compute warps wanted them.)
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);   // K-major x K-major, N = 128 queries
-      constexpr uint32_t idesc_nn = make_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major (dQ)
       const uint64_t k_desc = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
       const uint64_t v_desc = make_smem_desc_sw128(smem_u32(sV), 16, 1024);
       const uint64_t q_desc0 = make_smem_desc_sw128(smem_u32(sQ), 16, 1024);
       const uint64_t do_desc0 = make_smem_desc_sw128(smem_u32(sDO), 16, 1024);
-      const uint64_t k_desc_mn = make_smem_desc_sw128(smem_u32(sK), AB_TILE, 1024);
-      const uint64_t ds_desc_mn = make_smem_desc_sw128(smem_u32(sDS), AB_TILE, 1024);
       uint32_t g = 0;    // S^T / dP^T pairs issued so far
-      uint32_t gq = 0;   // dQ GEMMs issued so far
       uint32_t items = 0;
       for (int k = 0; k < rounds; ++k) {
         Item im;
         if (!get_item(k, im)) continue;
-        // K and V of this item: every GEMM that reads them is issued by this thread, so it also fetches them — as soon
-        // as the previous item's last dQ (committed to kv_empty below) has completed.  The producer warp meanwhile runs
-        // ahead with the Q / dO ring of this item.
+        // K and V of this item are fetched by this thread: it (and the dQ issuer) issue every GEMM that reads them,
+        // and both commit to kv_empty behind their last one of an item.  The producer warp meanwhile runs ahead with
+        // the Q / dO ring of this item.
         if (items > 0) mbar_wait(kv_empty, (items - 1) & 1);
         mbar_arrive_expect_tx(kv_full, 2 * AB_TILE);
         tma_load_2d(sK, &tmQKV, kv_full, d + im.h * AB_HD, static_cast<int>(im.krow0));
         tma_load_2d(sV, &tmQKV, kv_full, 2 * d + im.h * AB_HD, static_cast<int>(im.krow0));
         mbar_wait(kv_full, items & 1);
         ++items;
-        for (int it = 0; it <= im.n_it; ++it) {
-          if (it < im.n_it) {  // S^T / dP^T of step `it`
-            const uint32_t st = g % AB_STAGES;
-            const uint64_t q_desc = q_desc0 + st * (AB_TILE >> 4), do_desc = do_desc0 + st * (AB_TILE >> 4);
-            mbar_wait(&qdo_full[st], (g / AB_STAGES) & 1);
-            if (g > 0) mbar_wait(sdp_free, (g - 1) & 1);
-            tc_fence_after();
+        for (int it = 0; it < im.n_it; ++it, ++g) {
+          const uint32_t st = g % AB_STAGES;
+          const uint64_t q_desc = q_desc0 + st * (AB_TILE >> 4), do_desc = do_desc0 + st * (AB_TILE >> 4);
+          mbar_wait(&qdo_full[st], (g / AB_STAGES) & 1);
+          if (g > 0) mbar_wait(sdp_free, (g - 1) & 1);
+          tc_fence_after();
 #pragma unroll
-            for (int kk = 0; kk < AB_HD / 16; ++kk) {
-              umma_ss(tS, k_desc + kk * 2, q_desc + kk * 2, idesc_s, kk > 0 ? 1u : 0u);
-              umma_ss(tDP, v_desc + kk * 2, do_desc + kk * 2, idesc_s, kk > 0 ? 1u : 0u);
-            }
-            umma_commit(s_full);
-            ++g;
+          for (int kk = 0; kk < AB_HD / 16; ++kk) {
+            umma_ss(tS, k_desc + kk * 2, q_desc + kk * 2, idesc_s, kk > 0 ? 1u : 0u);
+            umma_ss(tDP, v_desc + kk * 2, do_desc + kk * 2, idesc_s, kk > 0 ? 1u : 0u);
           }
-          if (it > 0) {  // dQ of step it-1
-            mbar_wait(pds_ready, gq & 1);
-            if (gq > 0) mbar_wait(dq_empty, (gq - 1) & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int kk = 0; kk < AB_T / 16; ++kk)
-              umma_ss(tDQ, ds_desc_mn + kk * (2048 >> 4), k_desc_mn + kk * (2048 >> 4), idesc_nn, kk > 0 ? 1u : 0u);
-            umma_commit(dq_full);
-            umma_commit(mma_done);
-            ++gq;
-          }
+          umma_commit(s_full);
         }
         umma_commit(kv_empty);
       }
     }
-  } else if (warp == AB_W_MMA_DV) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AB_REGS_AUX));
+  } else if (warp == ABP_W_MMA_DV) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ABP_REGS_AUX));
     // ------------------------------------------------------------ MMA issuer 2: dV += P^T dO (A = P^T from tensor memory)
     if (lane == 0) {
       constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);   // A K-major (TMEM), B MN-major, N = 64
@@ -743,8 +735,8 @@ attn_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         ++items;
       }
     }
-  } else if (warp == AB_W_MMA_DK) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AB_REGS_AUX));
+  } else if (warp == ABP_W_MMA_DK) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ABP_REGS_AUX));
     // ------------------------------------------------------------ MMA issuer 3: dK += dS^T Q
     if (lane == 0) {
       constexpr uint32_t idesc_kn = make_idesc_bf16(128, 64, 0, 1);   // A K-major, B MN-major, N = 64
@@ -770,8 +762,8 @@ attn_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
         ++items;
       }
     }
-  } else if (warp >= AB_W_DRAIN) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AB_REGS_AUX));
+  } else if (warp >= ABP_W_DRAIN && warp < ABP_W_DRAIN + 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ABP_REGS_AUX));
     // ------------------------------------------------------------ dQ drain warps (one per TMEM lane quarter), off the
     // compute warps' serial chain: dQ_i of a step leaves tensor memory (-> dq_empty: the next dQ GEMM may start), is
     // staged as two 128B-swizzled [32 rows x 32] fp32 blocks and added into dq_acc by two TMA bulk reduce-adds.
@@ -810,6 +802,32 @@ attn_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
       }
     }
     if (lane == 0) bulk_wait_group<0>();  // the reduce-adds have landed
+  } else if (warp >= ABP_W_MMA_DQ) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ABP_REGS_AUX));  // dQ issuer + padding warps
+if (warp == ABP_W_MMA_DQ && lane == 0) {
+      // ---------------------------------------------------------- MMA issuer 4: dQ = dS K.  A = the dS^T buffer read
+      // MN-major (M = queries, 64 per block, blocks AB_TILE apart), B = K MN-major.  Waits for the step's dS^T
+      // (pds_ready) and for the previous dQ to have left tensor memory (dq_empty, signalled by the drain warps).
+      constexpr uint32_t idesc_nn = make_idesc_bf16(128, 64, 1, 1);   // A MN-major, B MN-major
+      const uint64_t k_desc_mn = make_smem_desc_sw128(smem_u32(sK), AB_TILE, 1024);
+      const uint64_t ds_desc_mn = make_smem_desc_sw128(smem_u32(sDS), AB_TILE, 1024);
+      uint32_t gq = 0;
+      for (int k = 0; k < rounds; ++k) {
+        Item im;
+        if (!get_item(k, im)) continue;
+        for (int it = 0; it < im.n_it; ++it, ++gq) {
+          mbar_wait(pds_ready, gq & 1);
+          if (gq > 0) mbar_wait(dq_empty, (gq - 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < AB_T / 16; ++kk)
+            umma_ss(tDQ, ds_desc_mn + kk * (2048 >> 4), k_desc_mn + kk * (2048 >> 4), idesc_nn, kk > 0 ? 1u : 0u);
+          umma_commit(dq_full);
+          umma_commit(mma_done);
+        }
+        umma_commit(kv_empty);
+      }
+    }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AB_REGS_COMPUTE));
     // ------------------------------------------------------------ compute warps (16): warp = (lane quarter, column quarter)
@@ -938,7 +956,7 @@ attn_bwd_persistent_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gr
 
   tc_fence_before();
   __syncthreads();
-  if (warp == AB_W_MMA_S) {
+  if (warp == ABP_W_MMA_S) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -1018,7 +1036,7 @@ extern "C" int plm_attn_bwd_variant(const void* qkv, const void* out, const void
   if (variant == 1) {
     const long long n_items = static_cast<long long>(grid.x) * H * B;
     const int ctas = static_cast<int>(n_items < sm_count() ? n_items : sm_count());
-    attn_bwd_persistent_kernel<<<ctas, AB_THREADS, AB_SMEM, stream>>>(
+    attn_bwd_persistent_kernel<<<ctas, ABP_THREADS, AB_SMEM, stream>>>(
         tmQKV, tmDO, tmDQ, lse, delta, seg_start, rope_table, static_cast<__nv_bfloat16*>(dqkv), dq_acc, T, H, B * H,
         scale, scale * 1.4426950408889634f);
   } else {

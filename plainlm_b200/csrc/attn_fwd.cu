@@ -30,7 +30,7 @@
 #include <mutex>
 
 #ifndef PLM_ATTN_FWD_DEFAULT_VARIANT
-#define PLM_ATTN_FWD_DEFAULT_VARIANT 0
+#define PLM_ATTN_FWD_DEFAULT_VARIANT 11
 #endif
 
 namespace plm {

@@ -109,7 +109,9 @@ class TorchEngine(torch.nn.Module):
     self.model = model.to(device)
     self.rt = self.model.runtime()
     self.reducer = None
-    if dist.is_initialized():
+    # optional cfg key `data_parallel: False`: build a replica-less engine inside a distributed job (bench.py uses it
+    # for the N ranks == 1 rank x N*accum equivalence check)
+    if dist.is_initialized() and getattr(cfg, 'data_parallel', True):
       broadcast_parameters(self.rt.flat)
       wire = torch.float32 if getattr(cfg, 'ddp_fp32_allreduce', False) else torch.bfloat16
       self.reducer = GradReducer(self.rt.flat, wire_dtype=wire)
