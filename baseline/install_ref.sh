@@ -18,6 +18,12 @@ rm -rf "$HERE/_ref"
 python -m pip install --quiet --no-index --no-build-isolation --no-deps --find-links /opt/wheelhouse \
   --target "$HERE/_ref" "$TMP"
 rm -rf "$TMP"
+# the driver scripts of the reference (not part of its wheel): train.py and the modules it imports from its own root.
+# tests/test_gpu_dropin_train.py runs this unmodified train.py twice — on the drop-in shims and on the reference itself.
+for f in train.py utils.py checkpoint_utils.py torch_utils.py; do
+  cp "$REF/$f" "$HERE/_ref/$f"
+  cmp -s "$HERE/_ref/$f" "$REF/$f" || { echo "MISMATCH $f"; exit 1; }
+done
 # byte-identity check of every installed source file against the reference tree
 ( cd "$HERE/_ref" && find data engine models optim -name '*.py' | while read -r f; do cmp -s "$f" "$REF/$f" || { echo "MISMATCH $f"; exit 1; }; done )
 find "$HERE/_ref" -name '__pycache__' -type d -prune -exec rm -rf {} +

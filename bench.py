@@ -167,7 +167,7 @@ def load_peaks():
 
 def op_work(name, tag, c, pairs_per_token=None):
   """Algorithmic work of one op call: ('tensor', flops) or ('hbm', bytes) — DESIGN.md §kernels."""
-  if name == 'gemm':
+  if name in ('gemm', 'lmhead_ce_fwd'):  # lmhead_ce_fwd = the LM-head GEMM with the cross-entropy forward in its epilogue
     M, N, K = tag[0], tag[1], tag[2]
     return 'tensor', 2.0 * M * N * K
   if name in ('attn_fwd', 'attn_bwd'):
@@ -179,7 +179,7 @@ def op_work(name, tag, c, pairs_per_token=None):
   # bytes per element of the op's FIRST tensor argument: swiglu_fwd's is u [M, 2F] (2 B read + 1 B written per u
   # element = 6 B per hidden element); swiglu_bwd's is dh [M, F] (dh 2 + u 4 + du 4 = 10 B per hidden element)
   per_elt = {'rmsnorm_fwd': 6, 'rmsnorm_bwd': 16, 'swiglu_fwd': 3, 'swiglu_bwd': 10, 'embed_fwd': 8, 'embed_bwd': 12,
-             'ce_fwd_bwd': 6, 'sumsq': 4, 'adamw_step': 30, 'signsgd_step': 22, 'cast_f32_bf16': 6,
+             'ce_fwd_bwd': 6, 'ce_grad': 4, 'sumsq': 4, 'adamw_step': 30, 'signsgd_step': 22, 'cast_f32_bf16': 6,
              'cast_bf16_f32': 6, 'colsum_accum': 4}.get(name, 4)
   return 'hbm', float(per_elt) * n
 

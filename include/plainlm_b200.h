@@ -28,7 +28,7 @@ extern "C" {
 #define PLM_ERR_CUDA (-2)        /* CUDA runtime / driver error while encoding a descriptor or launching */
 #define PLM_ERR_UNSUPPORTED (-3) /* shape outside what the sm_100a kernels implement                     */
 
-#define PLM_ABI_VERSION 3
+#define PLM_ABI_VERSION 4
 
 typedef void* plm_stream_t;
 
@@ -61,6 +61,12 @@ int plm_device_check(void);
  *                       (models/components.py:55-56: the GLU gate applied to fc1's output u = [a | z] while the tile is
  *                       still on chip; silu is evaluated on the bf16-rounded a, z exactly like plm_swiglu_fwd).
  *                       Needs b_kmajor = 1 and (N/2) % 128 == 0.
+ *   PLM_EPI_BF16_CE     C (bf16)  = acc (skipped when C == NULL)  AND  the cross-entropy statistics of the bf16-ROUNDED
+ *                       logits: ce_partial[tile, row] = base-2 (max, sum 2^(x log2e - max)) over the tile's valid columns,
+ *                       ce_tgt_logit[row] = C[row, ce_targets[row]] (rows whose target is ignored are left untouched).
+ *                       The LM head of models/transformer.py:114 fused with the forward half of
+ *                       engine/engine.py:110-112; normally reached through plm_lmhead_ce_fwd.  K-major A and B only.
+ * The fused forward epilogues (ROPE, SWIGLU, CE) exist for a_kmajor = b_kmajor = 1 only (PLM_ERR_UNSUPPORTED otherwise).
  * splits > 1 partitions K and is only legal with PLM_EPI_ATOMIC_F32.  splits <= 0 lets the library choose.
  */
 #define PLM_EPI_BF16 0
@@ -69,6 +75,7 @@ int plm_device_check(void);
 #define PLM_EPI_RESID_F32 3
 #define PLM_EPI_ATOMIC_F32 4
 #define PLM_EPI_BF16_SWIGLU 5
+#define PLM_EPI_BF16_CE 6
 
 typedef struct plm_gemm_args {
   const void* A; /* bf16 */
@@ -84,6 +91,9 @@ typedef struct plm_gemm_args {
   int32_t rope_cols, rope_T, head_dim;
   void* C2;     /* bf16 [M, N/2], PLM_EPI_BF16_SWIGLU only */
   int64_t ldc2; /* leading dimension of C2 (elements) */
+  const int64_t* ce_targets; /* PLM_EPI_BF16_CE: int64 [M] */
+  float* ce_partial;         /* PLM_EPI_BF16_CE: fp32 [plm_lmhead_ce_tiles(N), M, 2] */
+  float* ce_tgt_logit;       /* PLM_EPI_BF16_CE: fp32 [M] */
 } plm_gemm_args;
 
 int plm_gemm_bf16(const plm_gemm_args* args, plm_stream_t stream);
@@ -183,12 +193,35 @@ int plm_embed_bwd(const int64_t* ids, const float* dx, float* dW, int64_t rows, 
 int plm_ce_fwd_bwd(void* logits, const int64_t* targets, float* row_loss, float* row_lse, float* stats, int64_t rows,
                    int32_t V, int64_t ldl, float grad_scale, int32_t write_grad, plm_stream_t stream);
 
+/* LM head FUSED with the cross-entropy forward: models/transformer.py:114 (lm_head) + engine/engine.py:81,110-112.
+ * One tcgen05 GEMM h[rows, d] x W[V, d]^T whose epilogue (a) rounds each logits tile to bf16 and stores it to `logits`
+ * (bf16 [rows, ldl]; pass NULL for a loss-only forward — eval — and nothing of size [rows, V] is ever written), and
+ * (b) reduces, per row and 256-column tile, the online-softmax statistics of the rounded logits and picks out the target
+ * logit while the tile is on chip.  A finalize launch folds the plm_lmhead_ce_tiles(V) partials per row into row_lse /
+ * row_loss, a third one takes the fixed-order mean (stats as for plm_ce_fwd_bwd).  The loss needs NO pass over the
+ * [rows, V] logits.  Workspaces: partial fp32 [2 * plm_lmhead_ce_tiles(V) * rows] (16-byte aligned), tgt_logit fp32 [rows].
+ * h: bf16 [rows, ldh]; W: bf16 [V, ldw]. */
+int plm_lmhead_ce_tiles(int64_t V);
+int plm_lmhead_ce_fwd(const void* h, const void* W, const int64_t* targets, void* logits, int64_t ldl, float* partial,
+                      float* tgt_logit, float* row_loss, float* row_lse, float* stats, int64_t rows, int32_t d, int32_t V,
+                      int64_t ldh, int64_t ldw, plm_stream_t stream);
+/* Backward half: dlogits = (softmax - onehot) * grad_scale / n_valid written IN PLACE over the bf16 logits (one read +
+ * one write pass), from the row_lse / stats plm_lmhead_ce_fwd (or plm_ce_fwd_bwd) produced.  The two LM-head gradient
+ * GEMMs (dgrad, wgrad) then consume dlogits through plm_gemm_bf16. */
+int plm_ce_grad(void* logits, const int64_t* targets, const float* row_lse, const float* stats, int64_t rows, int32_t V,
+                int64_t ldl, float grad_scale, plm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------ optimizer path
  * out[0] (+)= sum of squares of a flat fp32 buffer: first pass of torch.nn.utils.clip_grad_norm_
  * (engine/engine.py:126-128).  Deterministic (fixed-order two-stage reduction) so every data-parallel rank derives
  * the bit-identical clip coefficient.  workspace: fp32 [PLM_SUMSQ_WORKSPACE]. */
 #define PLM_SUMSQ_WORKSPACE 1024
 int plm_sumsq(const float* g, int64_t n, float* workspace, float* out, int32_t accumulate, plm_stream_t stream);
+/* Data-parallel tail: dst[i] = float(src_bf16[i]) * scale for the whole all-reduced wire buffer AND out[0] = sum dst[i]^2
+ * in one pass (replaces one plm_cast_bf16_f32 per bucket + plm_sumsq; what DDP's bucket copy-back + clip_grad_norm_'s
+ * norm pass do at engine/engine.py:104-105,126-128).  Same fixed-order reduction as plm_sumsq. */
+int plm_unpack_sumsq(const void* src_bf16, float* dst, int64_t n, float scale, float* workspace, float* out,
+                     plm_stream_t stream);
 
 /* AdamW as built by optim/init_optim.py:13-21 (torch fused AdamW semantics), over a flat range:
  *   g' = g * clip,  clip = (max_norm > 0 && gnorm_sq) ? min(1, max_norm / (sqrt(*gnorm_sq) + 1e-6)) : 1

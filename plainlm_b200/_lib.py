@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libplainlm_b200.so')
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 
 PLM_OK = 0
-EPI_BF16, EPI_BF16_ROPE, EPI_F32, EPI_RESID_F32, EPI_ATOMIC_F32, EPI_BF16_SWIGLU = range(6)
+EPI_BF16, EPI_BF16_ROPE, EPI_F32, EPI_RESID_F32, EPI_ATOMIC_F32, EPI_BF16_SWIGLU, EPI_BF16_CE = range(7)
 SUMSQ_WORKSPACE = 1024
 ACT_SILU, ACT_RELU2 = 0, 1
 
@@ -27,6 +27,7 @@ class GemmArgs(ctypes.Structure):
     ('a_kmajor', c_int32), ('b_kmajor', c_int32), ('epilogue', c_int32), ('splits', c_int32),
     ('rope_cols', c_int32), ('rope_T', c_int32), ('head_dim', c_int32),
     ('C2', c_void_p), ('ldc2', c_int64),
+    ('ce_targets', c_void_p), ('ce_partial', c_void_p), ('ce_tgt_logit', c_void_p),
   ]  # fmt: skip
 
 
@@ -56,7 +57,11 @@ SIGNATURES = {
   'plm_embed_fwd': (c_int32, [_P, _P, _P, _I64, _I32, _I64, _P]),
   'plm_embed_bwd': (c_int32, [_P, _P, _P, _I64, _I32, _I64, _P]),
   'plm_ce_fwd_bwd': (c_int32, [_P, _P, _P, _P, _P, _I64, _I32, _I64, _F, _I32, _P]),
+  'plm_lmhead_ce_tiles': (c_int32, [_I64]),
+  'plm_lmhead_ce_fwd': (c_int32, [_P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I64, _I64, _P]),
+  'plm_ce_grad': (c_int32, [_P, _P, _P, _P, _I64, _I32, _I64, _F, _P]),
   'plm_sumsq': (c_int32, [_P, _I64, _P, _P, _I32, _P]),
+  'plm_unpack_sumsq': (c_int32, [_P, _P, _I64, _F, _P, _P, _P]),
   'plm_adamw_step': (c_int32, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _F, _P, _F, _P]),
   'plm_signsgd_step': (c_int32, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _I32, _P, _F, _P]),
   'plm_nadamw_step': (c_int32, [_P, _P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _F, _F, _F, _P, _F, _P]),
@@ -96,7 +101,7 @@ def load():
     fn = getattr(lib, name)  # AttributeError if the symbol is missing
     fn.restype = restype
     fn.argtypes = argtypes
-  if lib.plm_abi_version() != 3:
+  if lib.plm_abi_version() != 4:
     raise RuntimeError('libplainlm_b200.so ABI version mismatch')
   _lib = lib
   return lib

@@ -134,6 +134,28 @@ ce_grad_kernel(__nv_bfloat16* __restrict__ logits, const int64_t* __restrict__ t
   }
 }
 
+// Fused LM-head path: combine the per-(column tile, row) base-2 statistics the GEMM epilogue left in `partial`
+// ([tiles, rows] of (max, sum 2^(x log2e - max))) into row_lse (natural log) and row_loss.  One thread per row; for a
+// fixed tile consecutive threads read consecutive float2 -> coalesced.  Fixed order: deterministic.
+__global__ void __launch_bounds__(256)
+ce_finalize_kernel(const float2* __restrict__ partial, const float* __restrict__ tgt_logit,
+                   const int64_t* __restrict__ targets, float* __restrict__ row_loss, float* __restrict__ row_lse,
+                   int64_t rows, int tiles, int V) {
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  float m = -INFINITY, s = 0.f;
+  for (int j = 0; j < tiles; ++j) {
+    const float2 t = __ldg(partial + static_cast<int64_t>(j) * rows + row);
+    const float nm = fmaxf(m, t.x);
+    s = s * exp2f(m - nm) + t.y * exp2f(t.x - nm);
+    m = nm;
+  }
+  const float lse = (m + log2f(s)) * 0.6931471805599453f;
+  row_lse[row] = lse;
+  const int64_t tgt = targets[row];
+  row_loss[row] = ce_ignored(tgt, V) ? 0.f : lse - tgt_logit[row];
+}
+
 // ------------------------------------------------------------------------------------------- sum of squares
 constexpr int SUMSQ_BLOCKS = 592;  // 4 per SM; must be <= PLM_SUMSQ_WORKSPACE
 
@@ -151,6 +173,48 @@ sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float* __restrict__
   }
   if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
     const float v = g[(n4 << 2) + threadIdx.x];
+    s += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    partial[blockIdx.x] = t;
+  }
+}
+
+// Data-parallel tail (plainlm_b200/dp.py): the all-reduced bf16 wire buffer -> fp32 gradients AND the squared gradient
+// norm in ONE pass (2 B read + 4 B written per element) instead of an unpack pass per bucket plus a separate sumsq pass.
+// Same block -> chunk mapping and reduction order as sumsq_partial_kernel: bit-identical norm on every rank.
+__global__ void __launch_bounds__(256)
+unpack_sumsq_partial_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n, float scale,
+                            float* __restrict__ partial) {
+  __shared__ float red[8];
+  const int64_t n8 = n >> 3;
+  const int64_t per = (n8 + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = per * blockIdx.x, hi = min(n8, lo + per);
+  float s = 0.f;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src) + i);
+    float4 a, b;
+    a.x = bf16_lo(v.x) * scale;
+    a.y = bf16_hi(v.x) * scale;
+    a.z = bf16_lo(v.y) * scale;
+    a.w = bf16_hi(v.y) * scale;
+    b.x = bf16_lo(v.z) * scale;
+    b.y = bf16_hi(v.z) * scale;
+    b.z = bf16_lo(v.w) * scale;
+    b.w = bf16_hi(v.w) * scale;
+    s += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+    reinterpret_cast<float4*>(dst)[2 * i] = a;
+    reinterpret_cast<float4*>(dst)[2 * i + 1] = b;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const float v = __bfloat162float(src[(n8 << 3) + threadIdx.x]) * scale;
+    dst[(n8 << 3) + threadIdx.x] = v;
     s += v * v;
   }
 #pragma unroll
@@ -387,6 +451,55 @@ int plm_ce_fwd_bwd(void* logits, const int64_t* targets, float* row_loss, float*
   return rc;
 }
 
+int plm_lmhead_ce_fwd(const void* h, const void* W, const int64_t* targets, void* logits, int64_t ldl, float* partial,
+                      float* tgt_logit, float* row_loss, float* row_lse, float* stats, int64_t rows, int32_t d, int32_t V,
+                      int64_t ldh, int64_t ldw, plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(h);
+  PLM_REQUIRE(h && W && targets && partial && tgt_logit && row_loss && row_lse && stats, "lmhead_ce: null pointer");
+  PLM_REQUIRE(rows > 0 && rows < (1ll << 31) && V > 0 && d > 0, "lmhead_ce: bad size");
+  plm_gemm_args g = {};
+  g.A = h;
+  g.B = W;
+  g.C = logits;  // NULL: loss-only forward, nothing of size [rows, V] is written
+  g.M = rows;
+  g.N = V;
+  g.K = d;
+  g.lda = ldh;
+  g.ldb = ldw;
+  g.ldc = logits ? ldl : ((static_cast<int64_t>(V) + 7) & ~7ll);
+  g.a_kmajor = 1;
+  g.b_kmajor = 1;
+  g.epilogue = PLM_EPI_BF16_CE;
+  g.splits = 1;
+  g.ce_targets = targets;
+  g.ce_partial = partial;
+  g.ce_tgt_logit = tgt_logit;
+  int rc = plm_gemm_bf16(&g, stream_);
+  if (rc != PLM_OK) return rc;
+  const int tiles = plm_lmhead_ce_tiles(V);
+  ce_finalize_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float2*>(partial), tgt_logit, targets, row_loss, row_lse, rows, tiles, V);
+  rc = check_launch("ce_finalize");
+  if (rc != PLM_OK) return rc;
+  ce_reduce_kernel<<<1, 1024, 0, stream>>>(row_loss, targets, stats, rows, V);
+  return check_launch("ce_reduce");
+}
+
+int plm_ce_grad(void* logits, const int64_t* targets, const float* row_lse, const float* stats, int64_t rows, int32_t V,
+                int64_t ldl, float grad_scale, plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(logits);
+  PLM_REQUIRE(logits && targets && row_lse && stats, "ce_grad: null pointer");
+  PLM_REQUIRE(rows > 0 && rows < (1ll << 31) && V > 0 && ldl >= V, "ce_grad: bad size");
+  PLM_REQUIRE(V % 8 == 0 && ldl % 8 == 0 && aligned16(logits), "ce_grad: V, ldl must be multiples of 8, logits aligned");
+  ce_grad_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(static_cast<__nv_bfloat16*>(logits), targets, row_lse,
+                                                                  stats, V, ldl, grad_scale);
+  return check_launch("ce_grad");
+}
+
 int plm_sumsq(const float* g, int64_t n, float* workspace, float* out, int32_t accumulate, plm_stream_t stream_) {
   using namespace plm;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -398,6 +511,21 @@ int plm_sumsq(const float* g, int64_t n, float* workspace, float* out, int32_t a
   int rc = check_launch("sumsq_partial");
   if (rc != PLM_OK) return rc;
   sumsq_final_kernel<<<1, 32, 0, stream>>>(workspace, SUMSQ_BLOCKS, out, accumulate);
+  return check_launch("sumsq_final");
+}
+
+int plm_unpack_sumsq(const void* src_bf16, float* dst, int64_t n, float scale, float* workspace, float* out,
+                     plm_stream_t stream_) {
+  using namespace plm;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  PLM_ENSURE_CONTEXT(src_bf16);
+  PLM_REQUIRE(src_bf16 && dst && workspace && out && n >= 0, "unpack_sumsq: bad argument");
+  PLM_REQUIRE(aligned16(src_bf16) && aligned16(dst), "unpack_sumsq: misaligned pointer");
+  unpack_sumsq_partial_kernel<<<SUMSQ_BLOCKS, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src_bf16), dst, n, scale,
+                                                                 workspace);
+  int rc = check_launch("unpack_sumsq_partial");
+  if (rc != PLM_OK) return rc;
+  sumsq_final_kernel<<<1, 32, 0, stream>>>(workspace, SUMSQ_BLOCKS, out, 0);
   return check_launch("sumsq_final");
 }
 

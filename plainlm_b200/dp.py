@@ -7,8 +7,13 @@ buckets are contiguous ranges of the model's flat fp32 gradient buffer, in the o
   1. waits for the compute stream's event,
   2. packs the range to bf16 pre-scaled by 1/world  (plm_cast_f32_bf16),
   3. all-reduces it (NCCL SUM over NVLink/NVSwitch, torch.distributed is only the plumbing),
-  4. unpacks back into the fp32 gradient range       (plm_cast_bf16_f32),
-while the compute stream keeps running the rest of backward.  `finish()` joins the streams before clipping.
+while the compute stream keeps running the rest of backward.  `finish()` joins the streams and then makes ONE pass over
+the whole wire buffer that writes the averaged fp32 gradients back AND reduces their squared norm for the clip
+(plm_unpack_sumsq: 6 B/param at full HBM speed) — instead of one unpack kernel per bucket squeezed in beside the
+backward GEMMs plus a separate norm pass.  With the fp32 wire (or injected pack/unpack functions: the CPU/gloo tests)
+every bucket is unpacked right after its all-reduce, as DDP's bucket copy-back does.
+The whole sequence is stream-ordered and free of host synchronisation, so the last micro-step can be captured — NCCL
+calls included — in the runtime's CUDA graph (models/runtime.py).
 """
 
 import torch
@@ -43,6 +48,8 @@ class GradReducer:
       default_unpack = lambda s, d, sc: ops.cast_bf16_f32(s, d, sc)  # noqa: E731
     self.pack = pack or default_pack  # caller-injected functions (CPU/gloo tests) always win
     self.unpack = unpack or default_unpack
+    # bf16 wire with the library's own kernels: no per-bucket unpack, one fused unpack + norm pass in finish()
+    self.fused_tail = self.on_cuda and wire_dtype == torch.bfloat16 and pack is None and unpack is None
     self.comm_stream = torch.cuda.Stream(device=flat.grads.device) if self.on_cuda else None
     self._pending = []
     self.launched = 0
@@ -61,17 +68,34 @@ class GradReducer:
         self.comm_stream.wait_event(ev)
         self.pack(g, w, 1.0 / self.world)
         dist.all_reduce(w, op=dist.ReduceOp.SUM, group=self.group)
-        self.unpack(w, g, 1.0)
+        if not self.fused_tail:
+          self.unpack(w, g, 1.0)
     else:
       self.pack(g, w, 1.0 / self.world)
       dist.all_reduce(w, op=dist.ReduceOp.SUM, group=self.group)
       self.unpack(w, g, 1.0)
     self.launched += 1
 
-  def finish(self):
-    """Join: later work on the compute stream (grad-norm, optimizer) sees the reduced gradients."""
+  def join(self):
+    """Later work on the compute stream sees everything the comm stream has done (stream-ordered, capturable)."""
     if self.world == 1 or not self.on_cuda:
       return
     ev = torch.cuda.Event()
     ev.record(self.comm_stream)
     torch.cuda.current_stream().wait_event(ev)
+
+  def finish(self, sumsq_workspace=None, gnorm_sq=None, joined=False):
+    """Join, then (bf16 wire) write the averaged gradients back to the fp32 buffer.  With a workspace and an output
+    scalar the same pass also leaves ||g||^2 in gnorm_sq[0]; returns True when it did (the caller then skips its own
+    norm pass)."""
+    if self.world == 1:
+      return False
+    if not joined:
+      self.join()
+    if not self.fused_tail:
+      return False
+    if sumsq_workspace is not None and gnorm_sq is not None:
+      ops.unpack_sumsq(self.wire, self.flat.grads, sumsq_workspace, gnorm_sq)
+      return True
+    ops.cast_bf16_f32(self.wire, self.flat.grads, 1.0)
+    return False

@@ -17,6 +17,8 @@ What changes underneath (SURVEY.md §3.2 -> here):
     swallows the exception.
 """
 
+import os
+
 import torch
 from torch import distributed as dist
 
@@ -93,6 +95,8 @@ class TorchEngine(torch.nn.Module):
     self.dtype = cfg.dtype
     self.intra_doc_masking = getattr(cfg, 'intra_doc_masking', False)
     self.use_cuda_graphs = getattr(cfg, 'cuda_graphs', True)  # optional key: replay the micro-step from a CUDA graph
+    # optional key: also capture the data-parallel last micro-step (bucket packs + NCCL all-reduces) in a CUDA graph
+    self.dp_graph = getattr(cfg, 'dp_cuda_graph', os.environ.get('PLM_DP_GRAPH', '1') != '0')
     self.device = device
     if 'cuda' not in str(device):
       raise RuntimeError('plainlm_b200.TorchEngine needs a CUDA device (B200); there is no CPU path')
@@ -215,21 +219,29 @@ class TorchEngine(torch.nn.Module):
     last = self.accumulated_samples == self.accumulation_steps
     on_bucket = self.reducer.bucket_ready if (self.reducer is not None and last) else None
 
-    if self.use_cuda_graphs and on_bucket is None:
+    dp_last = self.reducer is not None and last
+    if self.use_cuda_graphs and (not dp_last or self.dp_graph):
+      # the data-parallel last micro-step is captured with its bucket hooks (pack + NCCL all-reduce on the comm stream)
       loss_val = self.rt.graphed_loss_and_backward(inputs, targets, seg_start,
-                                                   grad_scale=1.0 / self.accumulation_steps)
-    else:  # the data-parallel micro-step interleaves NCCL buckets with backward: launched eagerly
+                                                   grad_scale=1.0 / self.accumulation_steps,
+                                                   reducer=self.reducer if dp_last else None)
+    else:  # eager launches; the data-parallel micro-step interleaves NCCL buckets with backward
       loss_val = self.rt.loss_and_backward(inputs, targets, seg_start, grad_scale=1.0 / self.accumulation_steps,
                                            backward=True, on_bucket=on_bucket)
+      if dp_last:
+        self.reducer.join()
     self._record_loss(loss_val, self.accumulated_samples - 1)
 
     if last:
       self.accumulated_samples = 0
+      # the gradient norm is always computed: it clips when grad_clip is set (max_norm > 0) and, clip or not, gates the
+      # update kernels on the device (non-finite norm -> no update).  Data-parallel with the bf16 wire: the same pass
+      # that writes the averaged gradients back to fp32 reduces the norm (plm_unpack_sumsq).
+      norm_done = False
       if self.reducer is not None:
-        self.reducer.finish()
-      # the gradient norm is always computed (4 B/param): it clips when grad_clip is set (max_norm > 0) and, clip or
-      # not, gates the update kernels on the device (non-finite norm -> no update)
-      grad_sumsq(self.rt.flat, self._sumsq_ws, self._gnorm_sq)
+        norm_done = self.reducer.finish(self._sumsq_ws, self._gnorm_sq, joined=True)
+      if not norm_done:
+        grad_sumsq(self.rt.flat, self._sumsq_ws, self._gnorm_sq)
       clip = GradClip(self._gnorm_sq, self.grad_clip or 0.0)
       self.check_nan(wait=True)  # reference: raise before optimizer.step (engine.py:116-117 precedes :131)
       self.optimizer.step(grad_clip=clip)

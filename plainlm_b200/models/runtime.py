@@ -105,30 +105,53 @@ class FlatParams:
 
 
 class _Workspace:
-  def __init__(self, rt, B, T):
+  """Activation buffers of one (B, T) micro-batch shape.  train=True: everything backward needs is kept per layer.
+  train=False (eval): forward-only — the per-layer lists alias a handful of buffers, there are no backward temporaries
+  and no [M, V] logits buffer (the loss comes out of the LM-head GEMM's epilogue)."""
+
+  def __init__(self, rt, B, T, train=True):
     m = rt.model
     dev = rt.flat.params.device
     M, d, F, V, H, L = B * T, m.dim, m.hidden_dim, m.vocab_size, m.n_heads, m.n_layers
     e = lambda *shape, dtype=bf16: torch.empty(*shape, device=dev, dtype=dtype)  # noqa: E731
-    self.B, self.T, self.M = B, T, M
-    self.x = [e(M, d, dtype=f32) for _ in range(L + 1)]      # x[l] = input of layer l; x[L] = final stream
-    self.x_mid = [e(M, d, dtype=f32) for _ in range(L)]
-    self.h1 = [e(M, d) for _ in range(L)]
-    self.h2 = [e(M, d) for _ in range(L)]
-    self.rstd1 = [e(M, dtype=f32) for _ in range(L)]
-    self.rstd2 = [e(M, dtype=f32) for _ in range(L)]
-    self.qkv = [e(M, 3 * d) for _ in range(L)]
-    self.attn = [e(M, d) for _ in range(L)]
-    self.lse = [e(B, H, T, dtype=f32) for _ in range(L)]
+    self.B, self.T, self.M, self.train = B, T, M, train
     U = rt.fc1_out  # 2F for the GLU (u = [a | z]), F for the single-branch MLPs
-    self.u = [e(M, U) for _ in range(L)]
-    self.g = [e(M, F) for _ in range(L)]
+
+    def per_layer(n, *shape, dtype=bf16):
+      if train:
+        return [e(*shape, dtype=dtype) for _ in range(n)]
+      one = e(*shape, dtype=dtype)
+      return [one] * n
+
+    if train:
+      self.x = [e(M, d, dtype=f32) for _ in range(L + 1)]    # x[l] = input of layer l; x[L] = final stream
+    else:
+      two = [e(M, d, dtype=f32), e(M, d, dtype=f32)]           # layer l reads x[l], writes x[l + 1]: ping-pong
+      self.x = [two[l & 1] for l in range(L + 1)]
+    self.x_mid = per_layer(L, M, d, dtype=f32)
+    self.h1 = per_layer(L, M, d)
+    self.h2 = per_layer(L, M, d)
+    self.rstd1 = per_layer(L, M, dtype=f32)
+    self.rstd2 = per_layer(L, M, dtype=f32)
+    self.qkv = per_layer(L, M, 3 * d)
+    self.attn = per_layer(L, M, d)
+    self.lse = per_layer(L, B, H, T, dtype=f32)
+    self.u = per_layer(L, M, U)
+    self.g = per_layer(L, M, F)
     self.hf = e(M, d)
     self.rstd_f = e(M, dtype=f32)
-    self.logits = e(M, V)
+    # LM head + cross-entropy: per-(256-column tile, row) softmax statistics written by the GEMM epilogue, row results
+    self.ce_partial = e(2 * ops.lmhead_ce_tiles(V) * M, dtype=f32)
+    self.tgt_logit = e(M, dtype=f32)
     self.row_loss = e(M, dtype=f32)
     self.row_lse = e(M, dtype=f32)
     self.stats = torch.zeros(4, device=dev, dtype=f32)
+    self.graphs = {}
+    if not train:
+      return
+    # bf16 logits of the micro-batch: written once by the LM-head GEMM, turned into dlogits in place, read by the two
+    # LM-head gradient GEMMs (the only [M, V] buffer; DESIGN.md §3 explains why recomputing it instead loses)
+    self.logits = e(M, V)
     # backward temporaries
     self.dx = e(M, d, dtype=f32)
     self.dx_b2 = [e(M, d), e(M, d)]  # ping-pong: the side-stream wgrad of one branch reads it while the next is written
@@ -145,7 +168,6 @@ class _Workspace:
     self.ids = torch.zeros(B, T, device=dev, dtype=torch.int64)
     self.targets = torch.zeros(B, T, device=dev, dtype=torch.int64)
     self.seg = torch.zeros(B * T, device=dev, dtype=torch.int32)
-    self.graphs = {}
 
 
 class TrainRuntime:
@@ -175,16 +197,19 @@ class TrainRuntime:
     self.P = {n: p[n].data for n in p}
     self.L = L
 
-  def workspace(self, B, T):
-    """At most two shapes stay alive (train + eval).  Eviction is least-recently-used and never takes a workspace that
-    holds captured CUDA graphs (the training shape) while another candidate exists."""
-    key = (B, T)
+  def workspace(self, B, T, train=True):
+    """At most two workspaces stay alive (normally the training shape + a forward-only eval one).  A training
+    workspace also serves an eval batch of the same shape.  Eviction is least-recently-used and never takes a workspace
+    that holds captured CUDA graphs while another candidate exists."""
+    key = (B, T, True)
+    if not train and key not in self._ws:
+      key = (B, T, False)
     ws = self._ws.pop(key, None)
     if ws is None:
       if len(self._ws) >= 2:
         victims = [k for k, w in self._ws.items() if not w.graphs] or list(self._ws)
         self._ws.pop(victims[0])
-      ws = _Workspace(self, B, T)
+      ws = _Workspace(self, B, T, train=key[2])
     self._ws[key] = ws  # re-insert: dict order = recency
     return ws
 
@@ -214,9 +239,19 @@ class TrainRuntime:
     return ws.hf
 
   def forward_logits(self, ids, seg_start, ws):
+    """Transformer.forward (models/transformer.py:108-114): plain LM-head GEMM, bf16 logits [M, V] (training workspace)."""
     self.forward_hidden(ids, seg_start, ws)
     ops.gemm(ws.hf, self.W['lm_head.weight'], ws.logits)
     return ws.logits
+
+  def forward_loss(self, ids, targets, seg_start, ws, keep_logits):
+    """Forward + mean cross-entropy with the LM head FUSED with the loss (transformer.py:114 + engine.py:110-112): the
+    softmax statistics and the target logit are reduced in the GEMM epilogue while each logits tile is on chip.  With
+    keep_logits the bf16 tile is also stored (backward turns it into dlogits in place); without, nothing of size
+    [M, V] is written at all.  Leaves [sum, n_valid, mean] in ws.stats."""
+    self.forward_hidden(ids, seg_start, ws)
+    ops.lmhead_ce_fwd(ws.hf, self.W['lm_head.weight'], targets.reshape(-1), ws.logits if keep_logits else None,
+                      ws.ce_partial, ws.tgt_logit, ws.row_loss, ws.row_lse, ws.stats, self.model.vocab_size)
 
   # ------------------------------------------------------------------------------------------ loss + backward
   def loss_and_backward(self, ids, targets, seg_start=None, grad_scale=1.0, backward=True, on_bucket=None):
@@ -225,21 +260,20 @@ class TrainRuntime:
     finalise gradient bucket i (data-parallel overlap hook)."""
     self.flat.refresh_if_stale()
     B, T = ids.shape
-    ws = self.workspace(B, T)
-    self.forward_logits(ids, seg_start, ws)
-    m = self.model
-    ops.ce_fwd_bwd(ws.logits, targets.reshape(-1), ws.row_loss, ws.row_lse, ws.stats, m.vocab_size,
-                   grad_scale=grad_scale, write_grad=backward)
+    ws = self.workspace(B, T, train=backward)
+    self.forward_loss(ids, targets, seg_start, ws, keep_logits=backward)
     loss = ws.stats[2].clone()
     if backward:
+      ops.ce_grad(ws.logits, targets.reshape(-1), ws.row_lse, ws.stats, self.model.vocab_size, grad_scale=grad_scale)
       self.backward_from_dlogits(ids, seg_start, ws, on_bucket)
     return loss
 
-  def graphed_loss_and_backward(self, ids, targets, seg_start=None, grad_scale=1.0):
-    """Same work as loss_and_backward(backward=True, on_bucket=None), replayed from a CUDA graph: the ~590 launches of
-    a micro-step are captured once per (shape, masked, grad_scale) and then cost one cudaGraphLaunch — no per-kernel
+  def graphed_loss_and_backward(self, ids, targets, seg_start=None, grad_scale=1.0, reducer=None):
+    """Same work as loss_and_backward(backward=True), replayed from a CUDA graph: the ~590 launches of a micro-step are
+    captured once per (shape, masked, grad_scale, data-parallel) and then cost one cudaGraphLaunch — no per-kernel
     host work, no launch gaps.  Inputs are copied into static device buffers (stream-ordered, so the previous replay
-    has finished reading them)."""
+    has finished reading them).  With a `reducer` (the last micro-step of a data-parallel step) the bucket hooks — pack,
+    NCCL all-reduce on the comm stream — are captured in the same graph and joined before it ends."""
     self.flat.refresh_if_stale()
     B, T = ids.shape
     ws = self.workspace(B, T)
@@ -248,7 +282,7 @@ class TrainRuntime:
     masked = seg_start is not None
     if masked:
       ws.seg.copy_(seg_start.reshape(-1), non_blocking=True)
-    key = (masked, float(grad_scale))
+    key = (masked, float(grad_scale), reducer is not None)
     rec = ws.graphs.get(key)
     seg = ws.seg if masked else None
     if rec is None:
@@ -257,7 +291,7 @@ class TrainRuntime:
       side.wait_stream(cur)
       with torch.cuda.stream(side):
         saved = self.flat.grads.clone()  # the warm-up / capture runs must not leak into the accumulated gradients
-        self._micro_step(ws, seg, grad_scale)  # warm-up: lazy one-time initialisation happens outside the capture
+        self._micro_step(ws, seg, grad_scale, reducer)  # warm-up: lazy one-time initialisation happens outside the capture
         graph = torch.cuda.CUDAGraph()
         n0 = ops.LAUNCHES
         try:
@@ -265,7 +299,7 @@ class TrainRuntime:
           # with pin_memory=True (data/dataloaders.py), whose pin-memory thread calls cudaHostAlloc at any time; under
           # the default 'global' mode that would abort the capture (or make the pin thread fail).
           with torch.cuda.graph(graph, stream=side, capture_error_mode='thread_local'):
-            self._micro_step(ws, seg, grad_scale)
+            self._micro_step(ws, seg, grad_scale, reducer)
           rec = (graph, ops.LAUNCHES - n0)
         except RuntimeError as e:  # capture refused: run this (shape, mask, scale) eagerly from now on
           print(f'plainlm_b200: CUDA graph capture failed ({str(e).splitlines()[0]}); falling back to eager launches')
@@ -276,18 +310,19 @@ class TrainRuntime:
       cur.wait_stream(side)
       ws.graphs[key] = rec
     if rec == 'eager':
-      self._micro_step(ws, seg, grad_scale)
+      self._micro_step(ws, seg, grad_scale, reducer)
       return ws.stats[2].clone()
     graph, launches = rec
     graph.replay()
     ops.LAUNCHES += launches
     return ws.stats[2].clone()
 
-  def _micro_step(self, ws, seg, grad_scale):
-    self.forward_logits(ws.ids, seg, ws)
-    ops.ce_fwd_bwd(ws.logits, ws.targets.reshape(-1), ws.row_loss, ws.row_lse, ws.stats, self.model.vocab_size,
-                   grad_scale=grad_scale, write_grad=True)
-    self.backward_from_dlogits(ws.ids, seg, ws, None)
+  def _micro_step(self, ws, seg, grad_scale, reducer=None):
+    self.forward_loss(ws.ids, ws.targets, seg, ws, keep_logits=True)
+    ops.ce_grad(ws.logits, ws.targets.reshape(-1), ws.row_lse, ws.stats, self.model.vocab_size, grad_scale=grad_scale)
+    self.backward_from_dlogits(ws.ids, seg, ws, reducer.bucket_ready if reducer is not None else None)
+    if reducer is not None:
+      reducer.join()  # the comm stream's work is ordered before whatever follows the micro-step (and closes the capture)
 
   def _wgrad(self, dy, x, name, guard):
     """grad[name] += dy^T x  (contraction over tokens, both operands read in place as MN-major), on the side stream:
@@ -340,7 +375,7 @@ class TrainRuntime:
       self._release(f'dx_b{flip}')
       return ws.dx_b2[flip]
 
-    dlogits = ws.logits  # overwritten in place by the CE kernel
+    dlogits = ws.logits  # overwritten in place by plm_ce_grad
     self._dgrad(dlogits, 'lm_head.weight', ws.dh)
     self._wgrad(dlogits, ws.hf, 'lm_head.weight', 'logits')
     if not self.tied:

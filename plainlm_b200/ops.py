@@ -48,7 +48,7 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_BF16, res
   N, Kb = (b.shape[0], b.shape[1]) if b_kmajor else (b.shape[1], b.shape[0])
   if K != Kb or out.shape[0] != M or out.shape[1] != N:
     raise ValueError(f'plainlm_b200.gemm: shape mismatch a={tuple(a.shape)} b={tuple(b.shape)} out={tuple(out.shape)}')
-  out_dtype = bf16 if epilogue in (_lib.EPI_BF16, _lib.EPI_BF16_ROPE, _lib.EPI_BF16_SWIGLU) else f32
+  out_dtype = bf16 if epilogue in (_lib.EPI_BF16, _lib.EPI_BF16_ROPE, _lib.EPI_BF16_SWIGLU, _lib.EPI_BF16_CE) else f32
   args = GemmArgs()
   args.A, args.B, args.C = _ptr(a, bf16, 'a'), _ptr(b, bf16, 'b'), _ptr(out, out_dtype, 'out')
   if residual is not None:
@@ -209,11 +209,53 @@ def ce_fwd_bwd(logits, targets, row_loss, row_lse, stats, V, grad_scale=1.0, wri
   return stats
 
 
+def lmhead_ce_tiles(V):
+  return int(_lib.load().plm_lmhead_ce_tiles(V))
+
+
+def lmhead_ce_fwd(h, w, targets, logits, partial, tgt_logit, row_loss, row_lse, stats, V):
+  """LM head fused with the cross-entropy forward (plm_lmhead_ce_fwd): h bf16 [rows, d] x w bf16 [V, d]^T; the loss
+  statistics come out of the GEMM epilogue.  logits: bf16 [rows, ld >= V] or None (loss-only forward: nothing of size
+  [rows, V] is written).  partial: fp32 [2 * lmhead_ce_tiles(V) * rows]; tgt_logit/row_loss/row_lse: fp32 [rows];
+  stats: fp32[4] -> [sum, n_valid, mean]."""
+  lib = _lib.load()
+  rows, d = h.shape
+  if w.shape[0] != V or w.shape[1] != d:
+    raise ValueError(f'plainlm_b200.lmhead_ce_fwd: weight {tuple(w.shape)} does not match V={V}, d={d}')
+  if partial.numel() < 2 * lmhead_ce_tiles(V) * rows or min(tgt_logit.numel(), row_loss.numel(), row_lse.numel()) < rows:
+    raise ValueError('plainlm_b200.lmhead_ce_fwd: workspace too small')
+  if logits is not None and (logits.shape[0] != rows or logits.shape[1] < V):
+    raise ValueError('plainlm_b200.lmhead_ce_fwd: logits must be [rows, >= V]')
+  check(lib.plm_lmhead_ce_fwd(_ptr(h, bf16, 'h'), _ptr(w, bf16, 'w'), _ptr(targets, torch.int64, 'targets'),
+                              _ptr(logits, bf16, 'logits'), _rowmajor_ld(logits, 'logits') if logits is not None else 0,
+                              _ptr(partial, f32, 'partial'), _ptr(tgt_logit, f32, 'tgt_logit'),
+                              _ptr(row_loss, f32, 'row_loss'), _ptr(row_lse, f32, 'row_lse'), _ptr(stats, f32, 'stats'),
+                              rows, d, V, _rowmajor_ld(h, 'h'), _rowmajor_ld(w, 'w'), _stream()), 'plm_lmhead_ce_fwd')
+  return stats
+
+
+def ce_grad(logits, targets, row_lse, stats, V, grad_scale=1.0):
+  """logits (bf16 [rows, ld >= V]) -> dlogits = (softmax - onehot) * grad_scale / n_valid, in place."""
+  lib = _lib.load()
+  check(lib.plm_ce_grad(_ptr(logits, bf16, 'logits'), _ptr(targets, torch.int64, 'targets'), _ptr(row_lse, f32, 'row_lse'),
+                        _ptr(stats, f32, 'stats'), logits.shape[0], V, _rowmajor_ld(logits, 'logits'), float(grad_scale),
+                        _stream()), 'plm_ce_grad')
+  return logits
+
+
 # ---------------------------------------------------------------------------------------------- optimizer path
 def sumsq(g, workspace, out, accumulate=False):
   lib = _lib.load()
   check(lib.plm_sumsq(_ptr(g, f32, 'g'), g.numel(), _ptr(workspace, f32, 'workspace'), _ptr(out, f32, 'out'),
                       int(accumulate), _stream()), 'plm_sumsq')
+  return out
+
+
+def unpack_sumsq(src, dst, workspace, out, scale=1.0):
+  """dst (fp32) = src (bf16) * scale over the whole buffer and out[0] = ||dst||^2, one pass (plm_unpack_sumsq)."""
+  lib = _lib.load()
+  check(lib.plm_unpack_sumsq(_ptr(src, bf16, 'src'), _ptr(dst, f32, 'dst'), src.numel(), float(scale),
+                             _ptr(workspace, f32, 'workspace'), _ptr(out, f32, 'out'), _stream()), 'plm_unpack_sumsq')
   return out
 
 
@@ -275,7 +317,7 @@ def seg_start_from_lengths(lengths, offsets, seg_start, B, T):
 # `gpu_launches`).  Counting is always on (an integer add per call); event timing only when a Profiler is installed.
 KERNELS_PER_CALL = {
   'gemm': 1, 'attn_fwd': 1, 'attn_bwd': 3, 'rope_qk_': 1, 'rmsnorm_fwd': 1, 'rmsnorm_bwd': 1, 'colsum_accum': 1, 'colsum_accum_batched': 1,
-  'swiglu_fwd': 1, 'swiglu_bwd': 1, 'act_fwd': 1, 'act_bwd': 1, 'embed_fwd': 1, 'embed_bwd': 1, 'ce_fwd_bwd': 3, 'sumsq': 2, 'adamw_step': 1, 'nadamw_step': 1, 'sgd_step': 1,
+  'swiglu_fwd': 1, 'swiglu_bwd': 1, 'act_fwd': 1, 'act_bwd': 1, 'embed_fwd': 1, 'embed_bwd': 1, 'ce_fwd_bwd': 3, 'lmhead_ce_fwd': 3, 'ce_grad': 1, 'sumsq': 2, 'unpack_sumsq': 2, 'adamw_step': 1, 'nadamw_step': 1, 'sgd_step': 1,
   'signsgd_step': 1, 'cast_f32_bf16': 1, 'cast_bf16_f32': 1, 'seg_start_from_lengths': 1,
 }  # fmt: skip
 LAUNCHES = 0
@@ -313,6 +355,8 @@ def _describe(name, args, kwargs):
     M, K = (a.shape[0], a.shape[1]) if ak else (a.shape[1], a.shape[0])
     N = b.shape[0] if bk else b.shape[1]
     return (M, N, K, int(ak), int(bk), kwargs.get('epilogue', 0))
+  if name == 'lmhead_ce_fwd':
+    return (args[0].shape[0], args[1].shape[0], args[0].shape[1], args[3] is not None)
   if name in ('attn_fwd', 'attn_bwd'):
     idx = 3 if name == 'attn_fwd' else 7
     return tuple(args[idx : idx + 4]) + (kwargs.get('seg_start') is not None,)

@@ -330,6 +330,16 @@ def test_swiglu_embed_ce_casts_against_oracle():
   ops.cast_bf16_f32(dst, back, 2.0)
   assert torch.equal(back.cpu(), dst.cpu().float() * 2.0)
 
+  # data-parallel tail: bf16 wire -> fp32 gradients + squared norm in one pass, deterministic
+  wire = torch.randn(1_000_003, generator=g).to(bf16)
+  gdst = torch.full((1_000_003,), float('nan'), device=DEV)
+  wsu = torch.empty(_lib.SUMSQ_WORKSPACE, device=DEV)
+  n1, n2 = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+  ops.unpack_sumsq(wire.to(DEV), gdst, wsu, n1)
+  assert torch.equal(gdst.cpu(), wire.float())
+  ops.sumsq(gdst, wsu, n2)
+  assert torch.equal(n1, n2)  # same fixed-order reduction as plm_sumsq over the unpacked values
+
   gbuf = torch.randn(1_000_003, generator=g)
   ws = torch.empty(_lib.SUMSQ_WORKSPACE, device=DEV)
   o1, o2 = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
@@ -337,6 +347,49 @@ def test_swiglu_embed_ce_casts_against_oracle():
   ops.sumsq(gbuf.to(DEV), ws, o2)
   assert torch.equal(o1, o2)  # deterministic
   assert abs(o1.item() - gbuf.double().pow(2).sum().item()) <= F32_RTOL * o1.item()
+
+
+@pytest.mark.parametrize('rows,V,d,store', [(128, 256, 64, True), (200, 1000, 128, True), (333, 50280, 256, True),
+                                             (200, 1000, 128, False), (1024, 2056, 1024, True)])
+def test_lmhead_fused_cross_entropy_against_oracle(rows, V, d, store):
+  """plm_lmhead_ce_fwd (LM-head GEMM whose epilogue reduces the cross-entropy statistics) + plm_ce_grad against the
+  oracle's loss on the same bf16 operands: ragged last column tile (V % 256 != 0, V % 32 != 0), rows % 128 != 0,
+  ignore_index rows, targets in the first / last column, and the loss-only form that never writes [rows, V]."""
+  ops, _ = _ops()
+  g = torch.Generator().manual_seed(rows + V)
+  h = (torch.randn(rows, d, generator=g) * 1.5).to(bf16)
+  w = (torch.randn(V, d, generator=g) * (2.0 / d ** 0.5)).to(bf16)
+  tg = torch.randint(0, V, (rows,), generator=g)
+  tg[1], tg[2], tg[5], tg[rows - 1] = 0, V - 1, -100, -100
+  logits_ref = (h.float() @ w.float().t()).to(bf16)  # autocast: the Linear rounds to bf16, CrossEntropyLoss upcasts
+  lf = logits_ref.float().requires_grad_(True)
+  loss_ref = orc.loss_fn(lf, tg)
+  (loss_ref * 0.25).backward()
+  n_valid = rows - 2
+
+  tiles = ops.lmhead_ce_tiles(V)
+  assert tiles == (V + 255) // 256
+  ld = (V + 7) // 8 * 8
+  lg = torch.full((rows, ld), float('nan'), device=DEV, dtype=bf16)[:, :V] if store else None
+  partial = torch.empty(2 * tiles * rows, device=DEV)
+  tgl, rl, rlse = (torch.empty(rows, device=DEV) for _ in range(3))
+  stats = torch.zeros(4, device=DEV)
+  ops.lmhead_ce_fwd(h.to(DEV), w.to(DEV), tg.to(DEV), lg, partial, tgl, rl, rlse, stats, V)
+  assert stats[1].item() == n_valid
+  assert abs(stats[2].item() - loss_ref.item()) <= F32_RTOL * loss_ref.item(), (stats[2].item(), loss_ref.item())
+  lse_ref = torch.logsumexp(logits_ref.float(), dim=1)
+  assert_close(rlse, lse_ref, F32_RTOL, what='row lse')
+  assert rl[5].item() == 0.0 and rl[rows - 1].item() == 0.0  # ignored rows contribute nothing
+  if not store:
+    return
+  # the stored tile is the GEMM's bf16 rounding of the same fp32 accumulation: equal up to accumulation order
+  assert_close(lg, logits_ref, BF16_RTOL, what='logits')
+  # the loss the epilogue reduced must be the loss OF THE STORED (rounded) logits, to fp32 accuracy
+  loss_of_stored = orc.loss_fn(lg.float().cpu(), tg)
+  assert abs(stats[2].item() - loss_of_stored.item()) <= 2e-5 * loss_of_stored.item()
+  ops.ce_grad(lg, tg.to(DEV), rlse, stats, V, grad_scale=0.25)
+  assert_close(lg, lf.grad, BF16_RTOL, what='dlogits')
+  assert torch.count_nonzero(lg[5]).item() == 0
 
 
 def test_rope_kernel_against_reference_fixture(comp):

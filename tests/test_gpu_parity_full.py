@@ -152,6 +152,61 @@ def test_gemms_420m_shapes_sampled():
 
 
 # ------------------------------------------------------------------------------------------- multi-tile loss curve
+def test_lmhead_fused_cross_entropy_420m_shape():
+  """The 420M LM head as the train step runs it: M = 16384 tokens, V = 50280 (ragged 104-column last tile), d = 1024,
+  with ignore_index rows.  Loss within 1e-3 of the oracle's CrossEntropyLoss on the bf16-rounded logits of the same
+  operands; dlogits on sampled rows."""
+  from plainlm_b200 import ops
+
+  M, V, d = 16384, 50280, 1024
+  g = torch.Generator().manual_seed(50280)
+  h = torch.randn(M, d, generator=g).to(bf16)
+  w = (torch.randn(V, d, generator=g) * 0.05).to(bf16)
+  tg = torch.randint(0, V, (M,), generator=g)
+  tg[::97] = -100
+  tg[1], tg[2] = 0, V - 1
+  hd_, wd_ = h.to(DEV), w.to(DEV)
+  # oracle arithmetic (fp32 matmul of the bf16 operands -> bf16 -> fp32 cross-entropy), evaluated in row blocks
+  loss_sum, n_valid, lse_ref = 0.0, 0, torch.empty(M)
+  rows_chk = torch.tensor([0, 1, 2, 97, 4095, 8191, 16383])
+  grad_ref = {}
+  for r0 in range(0, M, 2048):
+    lg = (h[r0 : r0 + 2048].float() @ w.float().t()).to(bf16).float()
+    t = tg[r0 : r0 + 2048]
+    lse = torch.logsumexp(lg, dim=1)
+    lse_ref[r0 : r0 + 2048] = lse
+    ok = t >= 0
+    loss_sum += float((lse[ok] - lg[ok, t[ok]]).double().sum())
+    n_valid += int(ok.sum())
+    for r in rows_chk.tolist():
+      if r0 <= r < r0 + 2048:
+        p = torch.softmax(lg[r - r0], dim=0)
+        if tg[r] >= 0:
+          p[tg[r]] -= 1.0
+        else:
+          p.zero_()
+        grad_ref[r] = p
+  loss_ref = loss_sum / n_valid
+
+  tiles = ops.lmhead_ce_tiles(V)
+  logits = torch.empty(M, V, device=DEV, dtype=bf16)
+  partial = torch.empty(2 * tiles * M, device=DEV)
+  tgl, rl, rlse = (torch.empty(M, device=DEV) for _ in range(3))
+  stats = torch.zeros(4, device=DEV)
+  tgd = tg.to(DEV)
+  ops.lmhead_ce_fwd(hd_, wd_, tgd, logits, partial, tgl, rl, rlse, stats, V)
+  assert stats[1].item() == n_valid
+  assert abs(stats[2].item() - loss_ref) <= 1e-3 * loss_ref, (stats[2].item(), loss_ref)
+  assert_close(rlse, lse_ref, 1e-3, what='row lse')
+  # loss-only form: same statistics, nothing stored
+  stats2 = torch.zeros(4, device=DEV)
+  ops.lmhead_ce_fwd(hd_, wd_, tgd, None, partial, tgl, rl, rlse, stats2, V)
+  assert torch.equal(stats, stats2)  # deterministic, and independent of the store
+  ops.ce_grad(logits, tgd, rlse, stats, V, grad_scale=1.0)
+  for r, p in grad_ref.items():
+    assert_close(logits[r], p / n_valid, BF16_RTOL, what=f'dlogits row {r}')
+
+
 def test_loss_curve_multitile_vs_oracle():
   """d = 512, T = 512, 8 heads, 2 layers: attention runs 4 query tiles x up to 8 key subtiles per head, every GEMM
   several K blocks and N tiles.  30 optimizer steps (accumulation 2) against the oracle's bf16 restatement on the CPU

@@ -596,6 +596,68 @@ def case_bw_perf():
   return out
 
 
+def case_lmhead_ce(rows=300, V=1000, d=128):
+  """Small fused LM-head + cross-entropy instance (also the compute-sanitizer case of that epilogue)."""
+  import torch
+  from plainlm_b200 import ops
+
+  dev = 'cuda'
+  g = torch.Generator().manual_seed(5)
+  h = torch.randn(rows, d, generator=g).to(torch.bfloat16).to(dev)
+  w = (torch.randn(V, d, generator=g) * 0.2).to(torch.bfloat16).to(dev)
+  tg = torch.randint(0, V, (rows,), generator=g)
+  tg[3] = -100
+  tg = tg.to(dev)
+  tiles = ops.lmhead_ce_tiles(V)
+  logits = torch.empty(rows, V, device=dev, dtype=torch.bfloat16)
+  partial = torch.empty(2 * tiles * rows, device=dev)
+  tgl, rl, rlse = (torch.empty(rows, device=dev) for _ in range(3))
+  stats = torch.zeros(4, device=dev)
+  ops.lmhead_ce_fwd(h, w, tg, logits, partial, tgl, rl, rlse, stats, V)
+  ref_logits = (h.float() @ w.float().t()).to(torch.bfloat16).float()
+  ref = torch.nn.functional.cross_entropy(ref_logits, tg)
+  ops.ce_grad(logits, tg, rlse, stats, V, 0.5)
+  torch.cuda.synchronize()
+  return {'case': f'lmhead_ce rows{rows} V{V} d{d}', 'loss': stats[2].item(), 'ref': ref.item(),
+          'rel_to_max': abs(stats[2].item() - ref.item()) / ref.item(), 'nan': bool(torch.isnan(logits).any())}
+
+
+def case_lmhead_perf():
+  """420M LM head: unfused (GEMM + plm_ce_fwd_bwd) vs fused (plm_lmhead_ce_fwd + plm_ce_grad), and the loss-only form."""
+  import torch
+  from plainlm_b200 import ops
+
+  dev = 'cuda'
+  M, V, d = 16384, 50280, 1024
+  h = torch.randn(M, d, device=dev).to(torch.bfloat16)
+  w = (torch.randn(V, d, device=dev) * 0.05).to(torch.bfloat16)
+  tg = torch.randint(0, V, (M,), device=dev)
+  logits = torch.empty(M, V, device=dev, dtype=torch.bfloat16)
+  tiles = ops.lmhead_ce_tiles(V)
+  partial = torch.empty(2 * tiles * M, device=dev)
+  tgl, rl, rlse = (torch.empty(M, device=dev) for _ in range(3))
+  stats = torch.zeros(4, device=dev)
+  fl = 2.0 * M * V * d
+
+  def unfused():
+    ops.gemm(h, w, logits)
+    ops.ce_fwd_bwd(logits, tg, rl, rlse, stats, V, 1.0, True)
+
+  def fused():
+    ops.lmhead_ce_fwd(h, w, tg, logits, partial, tgl, rl, rlse, stats, V)
+    ops.ce_grad(logits, tg, rlse, stats, V, 1.0)
+
+  out = []
+  for name, fn in (('gemm only', lambda: ops.gemm(h, w, logits)),
+                   ('unfused: gemm + ce_fwd_bwd', unfused),
+                   ('fused fwd only (stores logits)', lambda: ops.lmhead_ce_fwd(h, w, tg, logits, partial, tgl, rl, rlse, stats, V)),
+                   ('fused: lmhead_ce_fwd + ce_grad', fused),
+                   ('fused loss-only (no [M,V] store)', lambda: ops.lmhead_ce_fwd(h, w, tg, None, partial, tgl, rl, rlse, stats, V))):
+    ms = _time(fn, 10)
+    out.append({'case': name, 'ms': round(ms, 4), 'gemm_tflops': round(fl / ms / 1e9, 1)})
+  return out
+
+
 def case_attn_perf():
   import torch
   from plainlm_b200 import ops
@@ -703,6 +765,9 @@ CASES['attn_bwd_ragged_persist'] = lambda: case_attn_bwd(2, 200, 2, variant=1)
 CASES['attn_bwd_many_items_persist'] = lambda: case_attn_bwd(3, 1024, 40, doc=True, rope=True, variant=1)
 CASES['bandwidth'] = case_bandwidth
 CASES['gemm_perf'] = case_gemm_perf
+CASES['lmhead_ce'] = case_lmhead_ce
+CASES['lmhead_ce_ragged'] = lambda: case_lmhead_ce(333, 50280, 64)
+CASES['lmhead_perf'] = case_lmhead_perf
 CASES['attn_perf'] = case_attn_perf
 CASES['bw_perf'] = case_bw_perf
 CASES['gemm_epi_perf'] = case_gemm_epi_perf
