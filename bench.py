@@ -438,10 +438,21 @@ def run_ours(args):
       out['gpu_eager_reference'] = gpu_ref
     if dp_equiv is not None:
       out['dp_equiv'] = dp_equiv
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
   if world > 1:
-    dist.barrier()
-    dist.destroy_process_group()
+    # teardown: graphs that captured NCCL collectives pin the communicator (destroy_process_group would wait for them),
+    # so they are released first; a watchdog keeps a wedged teardown from outliving the measurement
+    import threading
+
+    from plainlm_b200.torch_utils import destroy_ddp
+
+    del engine
+    t = threading.Thread(target=destroy_ddp, daemon=True)
+    t.start()
+    t.join(60)
+    sys.stdout.flush()
+    if t.is_alive():
+      os._exit(0)
 
 
 def reference_subprocess(config, device, steps, warmup, optim='adamw', timeout=1500):

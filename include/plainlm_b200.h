@@ -133,7 +133,8 @@ int plm_attn_bwd(const void* qkv, const void* out, const void* dout, const float
                  int32_t hd, plm_stream_t stream);
 
 /* Diagnostics / A-B measurement only: the same backward with an explicit kernel variant (0 = one CTA per (key tile, head,
- * batch), 1 = persistent CTAs; < 0 = the default plm_attn_bwd uses). */
+ * batch), v in 1..16 = CTAs that walk a list of (key tile, head, batch) items, v CTAs per SM (1 = persistent); < 0 = the
+ * default plm_attn_bwd uses). */
 int plm_attn_bwd_variant(const void* qkv, const void* out, const void* dout, const float* lse,
                          const int32_t* seg_start, const float* rope_table, void* dqkv, float* delta, float* dq_acc,
                          int32_t B, int32_t T, int32_t H, int32_t hd, int32_t variant, plm_stream_t stream);

@@ -974,7 +974,7 @@ extern "C" int plm_attn_bwd(const void* qkv, const void* out, const void* dout, 
   return plm_attn_bwd_variant(qkv, out, dout, lse, seg_start, rope_table, dqkv, delta, dq_acc, B, T, H, hd, -1, stream);
 }
 
-// variant: 0 = one CTA per (key tile, head, batch), 1 = persistent CTAs; < 0 = library default.
+// variant: 0 = one CTA per (key tile, head, batch), v >= 1 = item-walking CTAs, v per SM (1 = persistent); < 0 = default.
 extern "C" int plm_attn_bwd_variant(const void* qkv, const void* out, const void* dout, const float* lse,
                                     const int32_t* seg_start, const float* rope_table, void* dqkv, float* delta,
                                     float* dq_acc, int32_t B, int32_t T, int32_t H, int32_t hd, int32_t variant,
@@ -990,7 +990,7 @@ extern "C" int plm_attn_bwd_variant(const void* qkv, const void* out, const void
     });
     variant = dflt;
   }
-  PLM_REQUIRE(variant == 0 || variant == 1, "attn_bwd: variant %d out of range", variant);
+  PLM_REQUIRE(variant >= 0 && variant <= 16, "attn_bwd: variant %d out of range", variant);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   PLM_ENSURE_CONTEXT(qkv);
   PLM_REQUIRE(qkv && out && dout && lse && dqkv && delta && dq_acc, "attn_bwd: null pointer");
@@ -1033,9 +1033,13 @@ extern "C" int plm_attn_bwd_variant(const void* qkv, const void* out, const void
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(hd));
   dim3 grid((T + AB_T - 1) / AB_T, H, B);
-  if (variant == 1) {
+  if (variant >= 1) {
+    // variant v: v CTAs per SM over the kernel's lifetime (v = 1: fully persistent).  With v > 1 the CTAs retire in v
+    // waves, which lets GEMMs queued on another stream (the weight-gradient side stream) take over SMs between waves
+    // while each CTA still amortises its set-up over ~n_items / (v SMs) items.
     const long long n_items = static_cast<long long>(grid.x) * H * B;
-    const int ctas = static_cast<int>(n_items < sm_count() ? n_items : sm_count());
+    const long long want = static_cast<long long>(variant) * sm_count();
+    const int ctas = static_cast<int>(n_items < want ? n_items : want);
     attn_bwd_persistent_kernel<<<ctas, ABP_THREADS, AB_SMEM, stream>>>(
         tmQKV, tmDO, tmDQ, lse, delta, seg_start, rope_table, static_cast<__nv_bfloat16*>(dqkv), dq_acc, T, H, B * H,
         scale, scale * 1.4426950408889634f);

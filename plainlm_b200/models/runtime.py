@@ -14,13 +14,24 @@ Layout in HBM (M = B*T tokens, d model dim, F GLU hidden, V vocab):
                   x_mid fp32[M,d], h2 bf16[M,d], rstd2[M], u bf16[M,2F], g bf16[M,F]
 """
 
+import gc
 import os
+import weakref
 
 import torch
 from .. import _lib, ops
 
 bf16, f32 = torch.bfloat16, torch.float32
 _ALIGN = 64  # elements; keeps every parameter view 256-byte aligned
+_RUNTIMES = weakref.WeakSet()
+
+
+def release_all_graphs():
+  """Destroy every captured CUDA graph of every live runtime.  A graph that captured NCCL collectives (the data-parallel
+  last micro-step) keeps the communicator alive: destroy_process_group() blocks until such graphs are gone, so
+  torch_utils.destroy_ddp() and bench.py call this first."""
+  for rt in list(_RUNTIMES):
+    rt.release_graphs()
 
 
 def _bucket_param_names(model):
@@ -196,6 +207,17 @@ class TrainRuntime:
     self.G = {n: gr(n) for n in p}   # fp32 grad views
     self.P = {n: p[n].data for n in p}
     self.L = L
+    _RUNTIMES.add(self)
+
+  def release_graphs(self):
+    """Drop the captured micro-step graphs (they are re-captured on the next use)."""
+    had = False
+    for ws in self._ws.values():
+      had = had or bool(ws.graphs)
+      ws.graphs.clear()
+    if had:
+      torch.cuda.synchronize()
+      gc.collect()
 
   def workspace(self, B, T, train=True):
     """At most two workspaces stay alive (normally the training shape + a forward-only eval one).  A training

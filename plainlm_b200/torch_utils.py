@@ -47,6 +47,12 @@ def pytorch_setup(cfg):
 
 
 def destroy_ddp():
+  """reference: torch_utils.py:62-65.  CUDA graphs that captured NCCL collectives (the data-parallel last micro-step,
+  models/runtime.py) pin the communicator, and destroy_process_group() would wait for them forever: they go first."""
   if dist.is_initialized():
+    from .models.runtime import release_all_graphs
+
+    torch.cuda.synchronize()
+    release_all_graphs()
     dist.barrier()
     dist.destroy_process_group()

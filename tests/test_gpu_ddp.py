@@ -3,6 +3,7 @@ on the same rows, through TorchEngine + NCCL.  Run with `gpurun
 
 import os
 import socket
+import time
 from collections import namedtuple
 
 import pytest
@@ -57,8 +58,9 @@ def _worker(rank, world, port, fp32_wire, out):
   dist.all_gather_object(gathered, float(sum(v.double().sum() for v in sd.values())))
   if rank == 0:
     torch.save({'sd': sd, 'losses': losses, 'checksums': gathered}, out)
-  dist.barrier()
-  dist.destroy_process_group()
+  from plainlm_b200.torch_utils import destroy_ddp
+
+  destroy_ddp()  # releases the captured graphs (they hold NCCL collectives) before the process group goes
 
 
 @pytest.mark.parametrize('fp32_wire', [True, False])
@@ -73,7 +75,13 @@ def test_two_ranks_equal_one_rank_with_doubled_accumulation(tmp_path, fp32_wire)
   port = s.getsockname()[1]
   s.close()
   out = str(tmp_path / 'dp.pt')
-  mp.spawn(_worker, args=(2, port, fp32_wire, out), nprocs=2, join=True)
+  ctx = mp.spawn(_worker, args=(2, port, fp32_wire, out), nprocs=2, join=False)
+  deadline = time.time() + 240
+  while not ctx.join(timeout=5):
+    if time.time() > deadline:
+      for p in ctx.processes:
+        p.kill()
+      pytest.fail('data-parallel workers did not finish within 240 s')
   dp = torch.load(out)
   assert dp['checksums'][0] == dp['checksums'][1]  # replicas stay bit-identical
 

@@ -779,6 +779,7 @@ CASES['gemm_sustained'] = case_gemm_sustained
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--case', default=None)
+  ap.add_argument('--cases', default=None, help='comma-separated cases run in THIS process (compute-sanitizer runs)')
   ap.add_argument('--only', default=None, help='substring filter when running all')
   ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'kernel_check.json'))
   ap.add_argument('--timeout', type=int, default=150)
@@ -786,6 +787,11 @@ def main():
   if args.case:
     res = CASES[args.case]()
     print('RESULT ' + json.dumps(res))
+    return
+  if args.cases:
+    for name in args.cases.split(','):
+      res = CASES[name]()
+      print(f'RESULT {name} ' + json.dumps(res), flush=True)
     return
   os.makedirs(os.path.dirname(args.out), exist_ok=True)
   allres = {}
