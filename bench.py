@@ -82,7 +82,7 @@ def make_cfgs(c, steps_budget):
                    seq_len=c['seq_len'], expand='8/3', mlp_class='glu', tie_embeddings=False, model='transformer')
   train_cfg = dict(seq_len=c['seq_len'], grad_accumulation_steps=c['grad_accumulation_steps'], grad_clip=1.0,
                    dtype='bfloat16', intra_doc_masking=c['intra_doc_masking'], resume=False, torch_compile=False,
-                   weight_decay=0.1, optim=c['optim'], lr=3e-3, beta1=0.9, beta2=0.95, fused_optim=True,
+                   weight_decay=0.1, optim=c['optim'], lr=1e-4 if c['optim'] == 'signSGD' else 3e-3, beta1=0.9, beta2=0.95, fused_optim=True,
                    scheduler='warmup_cosine', warmup_steps=0.1, cooldown_steps=None, lr_start=0.0, lr_end=1e-5,
                    lr_end_pct=None, steps_budget=max(steps_budget, 10), dampening=0.0)
   nt = lambda d: namedtuple('Cfg', d.keys())(**d)  # noqa: E731
@@ -416,7 +416,7 @@ def run_ours(args):
       'ms_per_step': round(ms_value / K, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
       'dtype': 'bf16', 'data': 'synthetic',
       'config': {'workload': f'plainLM {args.config}: d{c["d_model"]} L{c["n_layers"]} H{c["n_heads"]} T{T} V{c["vocab_size"]}, '
-                             f'micro_batch {B} x accum {accum} per GPU, AdamW + clip 1.0, '
+                             f'micro_batch {B} x accum {accum} per GPU, {c["optim"]} + clip 1.0, '
                              f'{"document-masked" if c["intra_doc_masking"] else "causal"} attention',
                  'global_batch_tokens': tokens_per_step, 'seq_len': T, 'parallelism': f'dp{world}',
                  'l2': 'working set (>=14 GB of activations + 5 GB of optimizer state per step) >> 126 MB L2: no flush needed'},
@@ -544,9 +544,12 @@ def main():
   ap.add_argument('--warmup', type=int, default=None)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--config', default='420m', choices=sorted(CONFIGS))
+  ap.add_argument('--optim', default=None, choices=['adamw', 'signSGD', 'sgd', 'nadamw'], help='override the config optimizer')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-gpu-reference', action='store_true')
   args = ap.parse_args()
+  if args.optim:
+    CONFIGS[args.config] = dict(CONFIGS[args.config], optim=args.optim)
   if args.impl == 'reference':
     args.steps = 3 if args.steps is None else args.steps
     args.warmup = 1 if args.warmup is None else args.warmup
