@@ -19,7 +19,7 @@ python -m pip install --quiet --no-index --no-build-isolation --no-deps --find-l
   --target "$HERE/_ref" "$TMP"
 rm -rf "$TMP"
 # the driver scripts of the reference (not part of its wheel): train.py and the modules it imports from its own root.
-# tests/test_gpu_dropin_train.py runs this unmodified train.py twice — on the drop-in shims and on the reference itself.
+# tests/test_gpu_train_dropin.py runs this unmodified train.py twice — on the drop-in shims and on the reference itself.
 for f in train.py utils.py checkpoint_utils.py torch_utils.py; do
   cp "$REF/$f" "$HERE/_ref/$f"
   cmp -s "$HERE/_ref/$f" "$REF/$f" || { echo "MISMATCH $f"; exit 1; }

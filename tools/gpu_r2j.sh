@@ -4,7 +4,7 @@
 set -x
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_ddp.py tests/test_gpu_dropin_train.py -m gpu -q -x > gpurun_out/r2j_pytest.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_ddp.py tests/test_gpu_train_dropin.py -m gpu -q -x > gpurun_out/r2j_pytest.log 2>&1
 tail -25 gpurun_out/r2j_pytest.log
 run2() { timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $1 bench.py --gpus 2 --steps 8 --warmup 3; }
 PLM_DP_GRAPH=1 run2 29611 > gpurun_out/r2j_bench_n2_graph.json 2> gpurun_out/r2j_bench_n2_graph.err

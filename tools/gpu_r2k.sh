@@ -4,7 +4,7 @@
 set -x
 cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_dropin_train.py -m gpu -q -x > gpurun_out/r2k_pytest_dropin.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_train_dropin.py -m gpu -q -x > gpurun_out/r2k_pytest_dropin.log 2>&1
 tail -30 gpurun_out/r2k_pytest_dropin.log | cut -c1-400
 for v in 0 2 4 8; do
   PLM_ATTN_BWD_VARIANT=$v timeout 300 python bench.py --steps 8 --warmup 3 --no-cpu-baseline --no-gpu-reference > gpurun_out/r2k_bench_bwd$v.json 2> gpurun_out/r2k_bench_bwd$v.err
