@@ -42,6 +42,19 @@ elif which == 'gemm':
     ops.gemm(g, w2, xo, epilogue=_lib.EPI_RESID_F32, residual=res)                          # fc2 fwd + residual
     ops.gemm(du, w1, dx, a_kmajor=True, b_kmajor=False)                                     # dgrad (K,MN)
     ops.gemm(du, x, dw, a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ATOMIC_F32, splits=0)  # wgrad (MN,MN)
+elif which == 'lmhead':
+  V = 50280
+  h = torch.randn(M, d, device=dev).to(bf)
+  w = (torch.randn(V, d, device=dev) * 0.05).to(bf)
+  tg = torch.randint(0, V, (M,), device=dev)
+  logits = torch.empty(M, V, device=dev, dtype=bf)
+  partial = torch.empty(2 * ops.lmhead_ce_tiles(V) * M, device=dev)
+  tgl, rl, rlse = (torch.empty(M, device=dev) for _ in range(3))
+  stats = torch.zeros(4, device=dev)
+  for _ in range(2):
+    ops.lmhead_ce_fwd(h, w, tg, logits, partial, tgl, rl, rlse, stats, V)   # LM head + cross-entropy statistics
+    ops.ce_grad(logits, tg, rlse, stats, V, 1.0)                             # dlogits in place
+    ops.gemm(h, w, logits)                                                   # the plain LM-head GEMM, for comparison
 elif which == 'norm':
   x = torch.randn(M, d, device=dev)
   w = torch.ones(d, device=dev)
