@@ -76,6 +76,7 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   p.rope_cols = a->rope_cols;
   p.rope_T = a->rope_T;
   p.head_dim = a->head_dim;
+  p.rope_cached = 0;
   p.glu_F = glu ? static_cast<int>(a->N / 2) : 0;
   p.debug = gemm_env().debug;
   p.ce_targets = a->ce_targets;
@@ -155,6 +156,13 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
     rc = make_tmap_f32_2d(&tmC, a->C, a->M, a->N, a->ldc, BM, 32);
   if (rc != PLM_OK) return rc;
   tmC2 = tmC;
+  if (a->epilogue == PLM_EPI_BF16_ROPE && a->head_dim == 64 && a->rope_T % BM == 0) {
+    // the (cos,sin) rows of a 128-row block are contiguous table rows: cache them in shared memory through TMA
+    // (table viewed [rope_T, 64] fp32, boxes of 128 positions x 32 floats)
+    rc = make_tmap_f32_2d(&tmC2, a->rope_table, a->rope_T, 64, 64, BM, 32);
+    if (rc != PLM_OK) return rc;
+    p.rope_cached = 1;
+  }
   if (glu) {
     rc = make_tmap_bf16_2d(&tmC2, a->C2, a->M, a->N / 2, a->ldc2, BM, 64);
     if (rc != PLM_OK) return rc;

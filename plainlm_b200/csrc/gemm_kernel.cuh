@@ -52,6 +52,8 @@ struct GemmParams {
   int epilogue;
   int splits;
   int rope_cols, rope_T, head_dim;
+  int rope_cached;  // PLM_EPI_BF16_ROPE: 1 = the tile's 128 (cos,sin) rows are TMA-loaded into shared memory once per row block
+                    // (head_dim == 64, rope_T % 128 == 0); 0 = coalesced global fetch per sub-chunk
   int glu_F;  // PLM_EPI_BF16_SWIGLU: F = N/2; tile n covers gate columns [128n, 128n+128) and up columns F + the same
   int num_m, num_n, kblocks;
   int debug;      // only read when the library is compiled with -DPLM_GEMM_DEBUG (timing experiments: 1 = skip epilogue
@@ -67,16 +69,22 @@ struct GemmParams {
 
 // PAIR: the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 (M = 256) per K-step; each CTA's smem then holds
 // only its half of the B tile (N/2 rows), so a stage shrinks from 48 to 32 KB and the ring deepens from 4 to 6.
-template <int BN, bool PAIR>
+// The RoPE epilogue keeps the (cos,sin) rows of its 128-row block in shared memory (32 KB at head_dim 64) and pays for
+// them with one operand stage.
+constexpr int ROPE_TABLE_BYTES = 128 * 64 * 4;  // 128 positions x (32 pairs x (cos, sin)) fp32: two 128-byte-wide TMA boxes
+template <int BN, bool PAIR, int EPI>
 struct GemmCfg {
-  static constexpr int STAGES = (BN == 256 && !PAIR) ? 4 : 6;
+  static constexpr bool ROPE = (EPI == PLM_EPI_BF16_ROPE);
+  static constexpr bool WIDE = (BN == 256 && !PAIR);  // 48 KB stages
+  static constexpr int STAGES = WIDE ? (ROPE ? 3 : 4) : (ROPE ? 5 : 6);
   static constexpr int EPI_BUFS = 2;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BUFS * EPI_BUF_BYTES + BAR_BYTES + 1024;  // + alignment slack
+  static constexpr int AUX_BYTES = ROPE ? ROPE_TABLE_BYTES : 0;
+  static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BUFS * EPI_BUF_BYTES + AUX_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared-memory limit of sm_100");
 };
 
@@ -109,7 +117,7 @@ template <int EPI, int BN, bool A_K, bool B_K, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmParams p) {
-  using Cfg = GemmCfg<BN, PAIR>;
+  using Cfg = GemmCfg<BN, PAIR, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CL = PAIR ? 2 : 1;
   static_assert(!PAIR || BN == 256, "the CTA-pair MMA needs 256-wide tiles");
@@ -122,11 +130,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
   uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;  // staging tiles of the TMA-store epilogue
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_BUFS * EPI_BUF_BYTES);
+  uint8_t* sRope = sEpi + Cfg::EPI_BUFS * EPI_BUF_BYTES;  // RoPE kind: (cos,sin) rows of the current 128-row block
+  uint64_t* full = reinterpret_cast<uint64_t*>(sRope + Cfg::AUX_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rope_full = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rope_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -145,6 +155,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);  // PAIR: both CTAs' epilogues drain first
     }
+    mbar_init(rope_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -305,6 +316,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     };
     int it = 0;
     uint32_t chunk_no = 0;
+    // RoPE, cached table: every epilogue thread tracks (uniformly) which 128-row block's (cos,sin) rows sit in sRope and
+    // how many loads have been issued; the elected thread issues the loads — the first here, the others right after the
+    // last chunk of the previous tile, i.e. a whole main loop ahead of their use.
+    const bool rope_cached = (EPI == PLM_EPI_BF16_ROPE) && p.rope_cached && !(PLM_DBG(p) & 1);
+    int rope_m = -1;          // row block whose table rows are (being) loaded
+    uint32_t rope_loads = 0;  // loads issued so far (parity of rope_full)
+    auto rope_tile_needs = [&](int w2, int& m2) -> bool {  // does work item w2 rotate anything, and which row block?
+      if (w2 >= total) return false;
+      int n2, k0, k1;
+      decode_work<CL>(p, w2, rank, m2, n2, k0, k1);
+      return static_cast<int64_t>(n2) * BN < p.rope_cols;
+    };
+    auto rope_issue = [&](int m2) {  // elected thread: 128 positions x 64 floats as two 128-byte-wide boxes
+      const int pos0 = static_cast<int>((static_cast<int64_t>(m2) * BM) % p.rope_T);
+      mbar_arrive_expect_tx(rope_full, ROPE_TABLE_BYTES);
+      tma_load_2d(sRope, &tmC2, rope_full, 0, pos0);
+      tma_load_2d(sRope + ROPE_TABLE_BYTES / 2, &tmC2, rope_full, 32, pos0);
+    };
+    if (rope_cached) {
+      int m2;
+      if (rope_tile_needs(cluster_id, m2)) {
+        if (elected) rope_issue(m2);
+        rope_m = m2;
+        ++rope_loads;
+      }
+    }
     for (int w = cluster_id; w < total; w += num_clusters, ++it) {
       int m_blk, n_blk, kb0, kb1;
       decode_work<CL>(p, w, rank, m_blk, n_blk, kb0, kb1);
@@ -364,7 +401,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       float4 nxt[8];
-      if (EPI == PLM_EPI_BF16_ROPE || EPI == PLM_EPI_RESID_F32) fetch_aux(nxt, 0);
+      if ((EPI == PLM_EPI_BF16_ROPE && !rope_cached) || EPI == PLM_EPI_RESID_F32) fetch_aux(nxt, 0);
+      if (rope_cached && tile_col0 < p.rope_cols) {
+        if (rope_m != m_blk) {  // not prefetched (the previous tile's look-ahead saw another row block): load it now
+          if (elected) rope_issue(m_blk);
+          rope_m = m_blk;
+          ++rope_loads;
+        }
+        mbar_wait(rope_full, (rope_loads - 1) & 1);
+      }
       // cross-entropy statistics of this row over this tile's columns (base 2), and where its target column sits
       float ce_m = -INFINITY, ce_s = 0.f;
       int tgt_local = -1;
@@ -440,18 +485,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int sc = 2 * c + h;
             if (sc < n_sub) {  // warp-uniform
               const bool rope_on = is_rope && (tile_col0 + sc * 32 < p.rope_cols);
-              if (rope_on) {
+              if (rope_on && !rope_cached) {
                 stage_aux(buf, nxt);
                 __syncwarp();
               }
-              if (EPI == PLM_EPI_BF16_ROPE && sc + 1 < n_sub) fetch_aux(nxt, sc + 1);
+              if (EPI == PLM_EPI_BF16_ROPE && !rope_cached && sc + 1 < n_sub) fetch_aux(nxt, sc + 1);
               uint32_t r[32];
               tmem_ld32(t_row + sc * 32, r);
               tmem_ld_wait();
               if (rope_on) {
+                // this row's 16 (cos,sin) pairs: from the cached table (box 0 = pairs 0..15, box 1 = pairs 16..31 of the
+                // head; a 32-column sub-chunk starts at column 0 or 32 of a 64-wide head) or from the staged fetch
+                const uint8_t* cs_row = rope_cached
+                                            ? sRope + (((tile_col0 + sc * 32) & 32) ? ROPE_TABLE_BYTES / 2 : 0) + own_off
+                                            : buf + own_off;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                  const float4 cs = *reinterpret_cast<const float4*>(buf + own_off + ((i ^ own_sw) << 4));
+                  const float4 cs = *reinterpret_cast<const float4*>(cs_row + ((i ^ own_sw) << 4));
                   const float a0 = __uint_as_float(r[4 * i + 0]), b0 = __uint_as_float(r[4 * i + 1]);
                   const float a1 = __uint_as_float(r[4 * i + 2]), b1 = __uint_as_float(r[4 * i + 3]);
                   r[4 * i + 0] = __float_as_uint(a0 * cs.x - b0 * cs.y);
@@ -459,7 +509,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   r[4 * i + 2] = __float_as_uint(a1 * cs.z - b1 * cs.w);
                   r[4 * i + 3] = __float_as_uint(b1 * cs.z + a1 * cs.w);
                 }
-                __syncwarp();  // every lane has read its (cos,sin) row before the tile is overwritten
+                if (!rope_cached) __syncwarp();  // every lane has read its staged (cos,sin) row before the tile is overwritten
               }
 #pragma unroll
               for (int i = 0; i < 16; ++i)
@@ -481,13 +531,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   for (int i = 0; i < 32; ++i)
                     if (i >= valid) x[i] = -INFINITY;
                 }
-                float mx = x[0];
+                // four independent max / sum chains: a single 32-deep dependent chain per reduction made this epilogue
+                // longer than the main loop (ncu: tensor pipe 82 % active against 95 % for the plain LM-head GEMM)
+                float mx0 = x[0], mx1 = x[1], mx2 = x[2], mx3 = x[3];
 #pragma unroll
-                for (int i = 1; i < 32; ++i) mx = fmaxf(mx, x[i]);
+                for (int i = 4; i < 32; i += 4) {
+                  mx0 = fmaxf(mx0, x[i]);
+                  mx1 = fmaxf(mx1, x[i + 1]);
+                  mx2 = fmaxf(mx2, x[i + 2]);
+                  mx3 = fmaxf(mx3, x[i + 3]);
+                }
+                const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
                 const float m_new = fmaxf(ce_m, mx * LOG2E);
-                float acc = 0.f;
+                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc += ex2_approx(fmaf(x[i], LOG2E, -m_new));
+                for (int i = 0; i < 32; i += 4) {
+                  acc0 += ex2_approx(fmaf(x[i], LOG2E, -m_new));
+                  acc1 += ex2_approx(fmaf(x[i + 1], LOG2E, -m_new));
+                  acc2 += ex2_approx(fmaf(x[i + 2], LOG2E, -m_new));
+                  acc3 += ex2_approx(fmaf(x[i + 3], LOG2E, -m_new));
+                }
+                const float acc = (acc0 + acc1) + (acc2 + acc3);
                 ce_s = ce_s * ex2_approx(ce_m - m_new) + acc;
                 ce_m = m_new;
               }
@@ -517,6 +581,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if constexpr (EPI == PLM_EPI_BF16_CE) {
           const int64_t row = row_base + r_tile;
           if (row < p.M) p.ce_partial[static_cast<int64_t>(n_blk) * p.M + row] = make_float2(ce_m, ce_s);
+        }
+        if (rope_cached) {  // every thread is past its last read of sRope (the chunk barrier above): fetch the next
+                            // rotating tile's rows now, a whole main loop ahead of their use
+          int m2;
+          if (rope_tile_needs(w + num_clusters, m2) && m2 != rope_m) {
+            if (elected) rope_issue(m2);
+            rope_m = m2;
+            ++rope_loads;
+          }
         }
       } else {
 #pragma unroll 1
@@ -582,7 +655,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 template <int EPI, int BN, bool A_K, bool B_K, bool PAIR>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2,
                        const GemmParams& p, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, PAIR>;
+  using Cfg = GemmCfg<BN, PAIR, EPI>;
   constexpr int CL = PAIR ? 2 : 1;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
