@@ -69,14 +69,17 @@ struct GemmParams {
 
 // PAIR: the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 (M = 256) per K-step; each CTA's smem then holds
 // only its half of the B tile (N/2 rows), so a stage shrinks from 48 to 32 KB and the ring deepens from 4 to 6.
+// PAIR with BN = 128 (256 x 128 per pair) exists for outputs whose 256-wide tiling quantises badly over 74 pairs
+// (N = 1024: 256 tiles = 3.46 waves; 512 narrow tiles = 6.92).
 // The RoPE epilogue keeps the (cos,sin) rows of its 128-row block in shared memory (32 KB at head_dim 64) and pays for
 // them with one operand stage.
 constexpr int ROPE_TABLE_BYTES = 128 * 64 * 4;  // 128 positions x (32 pairs x (cos, sin)) fp32: two 128-byte-wide TMA boxes
 template <int BN, bool PAIR, int EPI>
 struct GemmCfg {
   static constexpr bool ROPE = (EPI == PLM_EPI_BF16_ROPE);
-  static constexpr bool WIDE = (BN == 256 && !PAIR);  // 48 KB stages
-  static constexpr int STAGES = WIDE ? (ROPE ? 3 : 4) : (ROPE ? 5 : 6);
+  static constexpr bool WIDE = (BN == 256 && !PAIR);    // 48 KB stages
+  static constexpr bool NARROW = (BN == 128 && PAIR);   // 24 KB stages: 256 x 128 per CTA pair
+  static constexpr int STAGES = WIDE ? (ROPE ? 3 : 4) : NARROW ? (ROPE ? 6 : 8) : (ROPE ? 5 : 6);
   static constexpr int EPI_BUFS = 2;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
@@ -120,7 +123,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   using Cfg = GemmCfg<BN, PAIR, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CL = PAIR ? 2 : 1;
-  static_assert(!PAIR || BN == 256, "the CTA-pair MMA needs 256-wide tiles");
   const int rank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
   const int cluster_id = blockIdx.x / CL;
   const int num_clusters = gridDim.x / CL;
@@ -697,6 +699,7 @@ int gemm_launch_epi(bool a_k, bool b_k, GemmTile tile, const CUtensorMap& tmA, c
                     const CUtensorMap& tmC, const CUtensorMap& tmC2, const GemmParams& p, cudaStream_t stream);
 
 #define PLM_GEMM_TILES_(EPI_, AK_, BK_)                                                             \
+  if (tile.pair && tile.bn == 128) return launch_gemm<EPI_, 128, AK_, BK_, true>(tmA, tmB, tmC, tmC2, p, stream); \
   if (tile.pair) return launch_gemm<EPI_, 256, AK_, BK_, true>(tmA, tmB, tmC, tmC2, p, stream);     \
   if (tile.bn == 256) return launch_gemm<EPI_, 256, AK_, BK_, false>(tmA, tmB, tmC, tmC2, p, stream); \
   return launch_gemm<EPI_, 128, AK_, BK_, false>(tmA, tmB, tmC, tmC2, p, stream);
