@@ -115,7 +115,7 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   int cl = (p.num_m >= 2 && bn == 256) ? 2 : 1;
   {
     const int forced = gemm_env().cluster;
-    if (forced == 1 || (forced == 2 && p.num_m >= 2 && !glu && !ce)) cl = forced;  // forced 2 with bn 128: narrow pair tiles
+    if (forced == 1 || (forced == 2 && bn == 256)) cl = forced;
     if (gemm_env().pair == 0) cl = 1;
   }
 

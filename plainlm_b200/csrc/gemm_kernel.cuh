@@ -77,9 +77,8 @@ constexpr int ROPE_TABLE_BYTES = 128 * 64 * 4;  // 128 positions x (32 pairs x (
 template <int BN, bool PAIR, int EPI>
 struct GemmCfg {
   static constexpr bool ROPE = (EPI == PLM_EPI_BF16_ROPE);
-  static constexpr bool WIDE = (BN == 256 && !PAIR);    // 48 KB stages
-  static constexpr bool NARROW = (BN == 128 && PAIR);   // 24 KB stages: 256 x 128 per CTA pair
-  static constexpr int STAGES = WIDE ? (ROPE ? 3 : 4) : NARROW ? (ROPE ? 6 : 8) : (ROPE ? 5 : 6);
+  static constexpr bool WIDE = (BN == 256 && !PAIR);  // 48 KB stages
+  static constexpr int STAGES = WIDE ? (ROPE ? 3 : 4) : (ROPE ? 5 : 6);
   static constexpr int EPI_BUFS = 2;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
@@ -123,6 +122,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   using Cfg = GemmCfg<BN, PAIR, EPI>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int CL = PAIR ? 2 : 1;
+  static_assert(!PAIR || BN == 256, "the CTA-pair MMA is instantiated for 256-wide tiles only");
   const int rank = (CL == 2) ? static_cast<int>(cluster_ctarank()) : 0;
   const int cluster_id = blockIdx.x / CL;
   const int num_clusters = gridDim.x / CL;
@@ -699,7 +699,6 @@ int gemm_launch_epi(bool a_k, bool b_k, GemmTile tile, const CUtensorMap& tmA, c
                     const CUtensorMap& tmC, const CUtensorMap& tmC2, const GemmParams& p, cudaStream_t stream);
 
 #define PLM_GEMM_TILES_(EPI_, AK_, BK_)                                                             \
-  if (tile.pair && tile.bn == 128) return launch_gemm<EPI_, 128, AK_, BK_, true>(tmA, tmB, tmC, tmC2, p, stream); \
   if (tile.pair) return launch_gemm<EPI_, 256, AK_, BK_, true>(tmA, tmB, tmC, tmC2, p, stream);     \
   if (tile.bn == 256) return launch_gemm<EPI_, 256, AK_, BK_, false>(tmA, tmB, tmC, tmC2, p, stream); \
   return launch_gemm<EPI_, 128, AK_, BK_, false>(tmA, tmB, tmC, tmC2, p, stream);

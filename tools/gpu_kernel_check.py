@@ -658,53 +658,6 @@ def case_lmhead_perf():
   return out
 
 
-def case_gemm_narrow_pair_probe():
-  """256 x 128 CTA-pair tiles (tuning bn=128, cluster=2) against the automatic choice on the N = 1024 outputs of the 420M
-  step (256 wide tiles = 3.46 waves over 74 pairs; 512 narrow ones = 6.92), with a correctness check of the narrow mode."""
-  import torch
-  from plainlm_b200 import ops, _lib
-
-  dev = 'cuda'
-  M, d, F = 16384, 1024, 2816
-  bf = torch.bfloat16
-  g0 = torch.Generator(device=dev).manual_seed(3)
-  rn = lambda *s: (torch.randn(*s, device=dev, generator=g0) * 0.5).to(bf)  # noqa: E731
-  x_d, x_F, x_3d, x_2F = rn(M, d), rn(M, F), rn(M, 3 * d), rn(M, 2 * F)
-  w_out, w2, wqkv, w1 = rn(d, d), rn(d, F), rn(3 * d, d), rn(2 * F, d)
-  res = torch.randn(M, d, device=dev, generator=g0)
-  o32 = torch.empty(M, d, device=dev)
-  obf = torch.empty(M, d, device=dev, dtype=bf)
-  shapes = [
-    ('out fwd+resid', lambda: ops.gemm(x_d, w_out, o32, epilogue=_lib.EPI_RESID_F32, residual=res), 2.0 * M * d * d,
-     lambda: x_d.float() @ w_out.float().t() + res, o32),
-    ('fc2 fwd+resid', lambda: ops.gemm(x_F, w2, o32, epilogue=_lib.EPI_RESID_F32, residual=res), 2.0 * M * d * F,
-     lambda: x_F.float() @ w2.float().t() + res, o32),
-    ('out dgrad', lambda: ops.gemm(x_d, w_out, obf, a_kmajor=True, b_kmajor=False), 2.0 * M * d * d,
-     lambda: x_d.float() @ w_out.float(), obf),
-    ('qkv dgrad', lambda: ops.gemm(x_3d, wqkv, obf, a_kmajor=True, b_kmajor=False), 2.0 * M * d * 3 * d,
-     lambda: x_3d.float() @ wqkv.float(), obf),
-    ('fc1 dgrad', lambda: ops.gemm(x_2F, w1, obf, a_kmajor=True, b_kmajor=False), 2.0 * M * d * 2 * F,
-     lambda: x_2F.float() @ w1.float(), obf),
-  ]
-  out = []
-  for name, fn, fl, ref_fn, dst in shapes:
-    rec = {'case': name}
-    for label, tune in (('auto', {}), ('narrow_pair', dict(bn=128, cluster=2)), ('bn256_pair', dict(bn=256, cluster=2)),
-                        ('bn128_single', dict(bn=128, cluster=1))):
-      _lib.gemm_tuning(**tune)
-      rec[label + '_us'] = round(_time(fn, 10) * 1e3, 1)
-      rec[label + '_tflops'] = round(fl / _time(fn, 10) / 1e9, 0)
-      if label == 'narrow_pair':
-        dst.fill_(float('nan'))
-        fn()
-        ref = ref_fn()
-        rec['narrow_rel_err'] = float((dst.float() - ref).abs().max() / ref.abs().max())
-        del ref
-    _lib.gemm_tuning()
-    out.append(rec)
-  return out
-
-
 def case_attn_perf():
   import torch
   from plainlm_b200 import ops
@@ -820,7 +773,6 @@ CASES['bw_perf'] = case_bw_perf
 CASES['gemm_epi_perf'] = case_gemm_epi_perf
 CASES['gemm_feed_probe'] = case_gemm_feed_probe
 CASES['gemm_n1024_probe'] = case_gemm_n1024_probe
-CASES['gemm_narrow_pair_probe'] = case_gemm_narrow_pair_probe
 CASES['gemm_sustained'] = case_gemm_sustained
 
 
