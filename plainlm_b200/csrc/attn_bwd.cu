@@ -66,14 +66,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// delta[b,h,t] = sum_c dO[t,h,c] * O[t,h,c].  8 lanes per (row, head): each lane 8 elements.
+// delta[b,h,t] = sum_c dO[t,h,c] * O[t,h,c].  8 lanes per (row, head): each lane 8 elements.  The same pass zeroes the
+// fp32 dQ accumulator (same [rows, H*64] element grid) that the main kernel reduce-adds into: one launch instead of a
+// memset node + a kernel per layer.
 __global__ void __launch_bounds__(256)
-attn_delta_kernel(const uint4* __restrict__ o, const uint4* __restrict__ dout, float* __restrict__ delta, int64_t rows,
-                  int T, int H) {
+attn_delta_kernel(const uint4* __restrict__ o, const uint4* __restrict__ dout, float* __restrict__ delta,
+                  float4* __restrict__ dq_acc, int64_t rows, int T, int H) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // one per 8 elements
   const int64_t total = rows * H * 8;
   float s = 0.f;
   if (idx < total) {
+    dq_acc[2 * idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dq_acc[2 * idx + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint4 a = __ldg(o + idx), g = __ldg(dout + idx);
     s = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
         bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
@@ -1021,13 +1025,11 @@ extern "C" int plm_attn_bwd_variant(const void* qkv, const void* out, const void
   rc = make_tmap_f32_2d(&tmDQ, dq_acc, rows, d, d, 32, 32);
   if (rc != PLM_OK) return rc;
 
-  cudaError_t e = cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * d * sizeof(float), stream);
-  if (e != cudaSuccess) return fail(PLM_ERR_CUDA, "attn_bwd memset: %s", cudaGetErrorString(e));
-
   {
     const int64_t n = rows * H * 8;
     attn_delta_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(
-        static_cast<const uint4*>(out), static_cast<const uint4*>(dout), delta, rows, T, H);
+        static_cast<const uint4*>(out), static_cast<const uint4*>(dout), delta, reinterpret_cast<float4*>(dq_acc), rows, T,
+        H);
     rc = check_launch("attn_delta");
     if (rc != PLM_OK) return rc;
   }
