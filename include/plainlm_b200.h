@@ -28,7 +28,7 @@ extern "C" {
 #define PLM_ERR_CUDA (-2)        /* CUDA runtime / driver error while encoding a descriptor or launching */
 #define PLM_ERR_UNSUPPORTED (-3) /* shape outside what the sm_100a kernels implement                     */
 
-#define PLM_ABI_VERSION 4
+#define PLM_ABI_VERSION 5
 
 typedef void* plm_stream_t;
 
@@ -66,6 +66,10 @@ int plm_device_check(void);
  *                       ce_tgt_logit[row] = C[row, ce_targets[row]] (rows whose target is ignored are left untouched).
  *                       The LM head of models/transformer.py:114 fused with the forward half of
  *                       engine/engine.py:110-112; normally reached through plm_lmhead_ce_fwd.  K-major A and B only.
+ *   PLM_EPI_BF16_GLU_BWD  fc2's input-gradient GEMM fused with the GLU backward (models/components.py:55-56, autograd of
+ *                       silu(a) * z): acc = dg [M, N = F]; C (bf16 [M, 2F], ld = ldc) = du = [dg z (s + a s (1 - s)) | dg a s]
+ *                       with s = sigmoid(a), a = C2[:, :F], z = C2[:, F:], C2 = the saved fc1 output u (bf16 [M, 2F],
+ *                       ld = ldc2).  dg is never written.  Needs a_kmajor = 1, b_kmajor = 0 and N %% 256 == 0.
  * The fused forward epilogues (ROPE, SWIGLU, CE) exist for a_kmajor = b_kmajor = 1 only (PLM_ERR_UNSUPPORTED otherwise).
  * splits > 1 partitions K and is only legal with PLM_EPI_ATOMIC_F32.  splits <= 0 lets the library choose.
  */
@@ -76,6 +80,7 @@ int plm_device_check(void);
 #define PLM_EPI_ATOMIC_F32 4
 #define PLM_EPI_BF16_SWIGLU 5
 #define PLM_EPI_BF16_CE 6
+#define PLM_EPI_BF16_GLU_BWD 7
 
 typedef struct plm_gemm_args {
   const void* A; /* bf16 */
@@ -89,7 +94,7 @@ typedef struct plm_gemm_args {
   int32_t epilogue;
   int32_t splits;
   int32_t rope_cols, rope_T, head_dim;
-  void* C2;     /* bf16 [M, N/2], PLM_EPI_BF16_SWIGLU only */
+  void* C2;     /* PLM_EPI_BF16_SWIGLU: output bf16 [M, N/2]; PLM_EPI_BF16_GLU_BWD: INPUT u, bf16 [M, 2N] */
   int64_t ldc2; /* leading dimension of C2 (elements) */
   const int64_t* ce_targets; /* PLM_EPI_BF16_CE: int64 [M] */
   float* ce_partial;         /* PLM_EPI_BF16_CE: fp32 [plm_lmhead_ce_tiles(N), M, 2] */

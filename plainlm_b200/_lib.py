@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libplainlm_b200.so')
 CSRC_DIR = os.path.join(_HERE, 'csrc')
 
 PLM_OK = 0
-EPI_BF16, EPI_BF16_ROPE, EPI_F32, EPI_RESID_F32, EPI_ATOMIC_F32, EPI_BF16_SWIGLU, EPI_BF16_CE = range(7)
+EPI_BF16, EPI_BF16_ROPE, EPI_F32, EPI_RESID_F32, EPI_ATOMIC_F32, EPI_BF16_SWIGLU, EPI_BF16_CE, EPI_BF16_GLU_BWD = range(8)
 SUMSQ_WORKSPACE = 1024
 ACT_SILU, ACT_RELU2 = 0, 1
 
@@ -101,7 +101,7 @@ def load():
     fn = getattr(lib, name)  # AttributeError if the symbol is missing
     fn.restype = restype
     fn.argtypes = argtypes
-  if lib.plm_abi_version() != 4:
+  if lib.plm_abi_version() != 5:
     raise RuntimeError('libplainlm_b200.so ABI version mismatch')
   _lib = lib
   return lib

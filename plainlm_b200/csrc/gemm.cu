@@ -42,12 +42,19 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   PLM_REQUIRE(aligned16(a->A) && aligned16(a->B) && aligned16(a->C), "gemm: operands must be 16-byte aligned");
   PLM_REQUIRE(a->N % 8 == 0 && a->lda % 8 == 0 && a->ldb % 8 == 0 && a->ldc % 8 == 0,
               "gemm: N and leading dimensions must be multiples of 8");
-  PLM_REQUIRE(a->epilogue >= PLM_EPI_BF16 && a->epilogue <= PLM_EPI_BF16_CE, "gemm: bad epilogue %d", a->epilogue);
+  PLM_REQUIRE(a->epilogue >= PLM_EPI_BF16 && a->epilogue <= PLM_EPI_BF16_GLU_BWD, "gemm: bad epilogue %d", a->epilogue);
   const bool glu = a->epilogue == PLM_EPI_BF16_SWIGLU;
   if (glu) {
     PLM_REQUIRE(a->b_kmajor != 0 && a->N % 256 == 0, "gemm: the SwiGLU epilogue needs a K-major B and N/2 %% 128 == 0");
     PLM_REQUIRE(a->C2 && aligned16(a->C2) && a->ldc2 % 8 == 0 && a->ldc2 >= a->N / 2,
                 "gemm: SwiGLU output C2 missing/misaligned");
+  }
+  const bool glub = a->epilogue == PLM_EPI_BF16_GLU_BWD;
+  if (glub) {
+    PLM_REQUIRE(a->a_kmajor != 0 && a->b_kmajor == 0 && a->N % 256 == 0,
+                "gemm: the GLU-backward epilogue needs a K-major A, an MN-major B and N %% 256 == 0");
+    PLM_REQUIRE(a->C2 && aligned16(a->C2) && a->ldc2 % 8 == 0 && a->ldc2 >= 2 * a->N && a->ldc >= 2 * a->N,
+                "gemm: GLU-backward input u / output du missing, misaligned or narrower than 2N");
   }
   if (ce) {
     PLM_REQUIRE(a->ce_targets && a->ce_partial && a->ce_tgt_logit && aligned16(a->ce_partial),
@@ -77,7 +84,7 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   p.rope_T = a->rope_T;
   p.head_dim = a->head_dim;
   p.rope_cached = 0;
-  p.glu_F = glu ? static_cast<int>(a->N / 2) : 0;
+  p.glu_F = glu ? static_cast<int>(a->N / 2) : (glub ? static_cast<int>(a->N) : 0);
   p.debug = gemm_env().debug;
   p.ce_targets = a->ce_targets;
   p.ce_partial = reinterpret_cast<float2*>(a->ce_partial);
@@ -99,6 +106,7 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
     if (forced == 128 || forced == 256) bn = forced;
   }
   if (glu) bn = 256;  // 128 gate + 128 up columns per tile
+  if (glub) bn = 256;  // a / z chunk pairs are cut from 256-wide tiles
   if (ce) bn = 256;   // the partial-statistics workspace is laid out for 256-column tiles (plm_lmhead_ce_partials)
   // Rasterisation: the ~148 tiles in flight should share the operand that does NOT fit in L2.  Walking M keeps one
   // B tile hot and streams A once per N-block (fine when A fits in L2); walking N reads each A row-block once.
@@ -150,7 +158,9 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   CUtensorMap tmA, tmB, tmC, tmC2;
   int rc;
   const void* c_base = a->C ? a->C : a->A;  // loss-only cross-entropy forward: the map is encoded but never stored through
-  if (a->epilogue == PLM_EPI_BF16 || a->epilogue == PLM_EPI_BF16_ROPE || glu || ce)
+  if (glub)  // du = [da | dz]: 2N columns
+    rc = make_tmap_bf16_2d(&tmC, a->C, a->M, 2 * a->N, a->ldc, BM, 64);
+  else if (a->epilogue == PLM_EPI_BF16 || a->epilogue == PLM_EPI_BF16_ROPE || glu || ce)
     rc = make_tmap_bf16_2d(&tmC, c_base, a->M, a->N, a->C ? a->ldc : a->lda, BM, 64);
   else
     rc = make_tmap_f32_2d(&tmC, a->C, a->M, a->N, a->ldc, BM, 32);
@@ -165,6 +175,10 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
   }
   if (glu) {
     rc = make_tmap_bf16_2d(&tmC2, a->C2, a->M, a->N / 2, a->ldc2, BM, 64);
+    if (rc != PLM_OK) return rc;
+  }
+  if (glub) {  // u = [a | z], loaded chunk-wise into the staging tiles
+    rc = make_tmap_bf16_2d(&tmC2, a->C2, a->M, 2 * a->N, a->ldc2, BM, 64);
     if (rc != PLM_OK) return rc;
   }
   if (a_k)
@@ -191,6 +205,8 @@ extern "C" int plm_gemm_bf16(const plm_gemm_args* a, plm_stream_t stream_) {
       return gemm_launch_epi<PLM_EPI_RESID_F32>(a_k, b_k, tile, tmA, tmB, tmC, tmC2, p, stream);
     case PLM_EPI_BF16_SWIGLU:
       return gemm_launch_epi<PLM_EPI_BF16_SWIGLU>(a_k, b_k, tile, tmA, tmB, tmC, tmC2, p, stream);
+    case PLM_EPI_BF16_GLU_BWD:
+      return gemm_launch_epi<PLM_EPI_BF16_GLU_BWD>(a_k, b_k, tile, tmA, tmB, tmC, tmC2, p, stream);
     default:
       return gemm_launch_epi<PLM_EPI_BF16_CE>(a_k, b_k, tile, tmA, tmB, tmC, tmC2, p, stream);
   }

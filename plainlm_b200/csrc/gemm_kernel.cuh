@@ -31,6 +31,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 #ifdef PLM_GEMM_DEBUG
 #define PLM_DBG(p_) ((p_).debug)
 #else
@@ -39,9 +45,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_EPI_WARPS = 4;   // one per TMEM lane quarter
+constexpr int GEMM_EPI_WARPS = 4;   // one per TMEM lane quarter ...
+// ... or two: the GLU backward runs EIGHT epilogue warps, the two warps of a lane quarter splitting every 64-column
+// chunk into its 32-column halves (105.5 -> 102.0 us at the 420M shape; that epilogue is bound by shared-memory
+// bandwidth — its a/z/da/dz tiles add 512 KB per output tile to the 1 MB the main loop already moves — not by issue
+// slots).  The cross-entropy kind has the same two-warp code path (EW == 8) but measured SLOWER with it when the logits
+// are stored (1.289 -> 1.337 ms; faster only in the loss-only form, 1.357 -> 1.253 ms), so it stays at four.
+template <int EPI>
+constexpr int epi_warps() {
+  return (EPI == PLM_EPI_BF16_GLU_BWD) ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS;
+}
 constexpr int EPI_BUF_BYTES = 128 * 128;  // staging tile: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
-constexpr int GEMM_THREADS = (2 + GEMM_EPI_WARPS) * 32;
 
 struct GemmParams {
   void* C;
@@ -72,20 +86,22 @@ struct GemmParams {
 // PAIR with BN = 128 (256 x 128 per pair) exists for outputs whose 256-wide tiling quantises badly over 74 pairs
 // (N = 1024: 256 tiles = 3.46 waves; 512 narrow tiles = 6.92).
 // The RoPE epilogue keeps the (cos,sin) rows of its 128-row block in shared memory (32 KB at head_dim 64) and pays for
-// them with one operand stage.
+// them with one operand stage; so does the GLU-backward epilogue for its second pair of (a, z) staging tiles.
 constexpr int ROPE_TABLE_BYTES = 128 * 64 * 4;  // 128 positions x (32 pairs x (cos, sin)) fp32: two 128-byte-wide TMA boxes
 template <int BN, bool PAIR, int EPI>
 struct GemmCfg {
   static constexpr bool ROPE = (EPI == PLM_EPI_BF16_ROPE);
+  static constexpr bool GLUB = (EPI == PLM_EPI_BF16_GLU_BWD);  // three (a, z) staging pairs instead of two staging tiles
   static constexpr bool WIDE = (BN == 256 && !PAIR);  // 48 KB stages
-  static constexpr int STAGES = WIDE ? (ROPE ? 3 : 4) : (ROPE ? 5 : 6);
-  static constexpr int EPI_BUFS = 2;
+  static constexpr int STAGES = WIDE ? (GLUB ? 2 : ROPE ? 3 : 4) : (GLUB ? 4 : ROPE ? 5 : 6);
+  static constexpr int GLUB_PAIRS = 3;
+  static constexpr int EPI_BUFS = GLUB ? 2 * GLUB_PAIRS : 2;
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
   static constexpr int AUX_BYTES = ROPE ? ROPE_TABLE_BYTES : 0;
-  static constexpr int BAR_BYTES = (2 * STAGES + 5) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * STAGES + 8) * 8 + 16;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BUFS * EPI_BUF_BYTES + AUX_BYTES + BAR_BYTES + 1024;  // + alignment slack
   static_assert(SMEM_BYTES <= 232448, "over the 227 KB shared-memory limit of sm_100");
 };
@@ -114,9 +130,9 @@ __device__ __forceinline__ void decode_work(const GemmParams& p, int w, int rank
 }
 
 // EPI: PLM_EPI_BF16 | PLM_EPI_BF16_ROPE | PLM_EPI_F32 (also serves PLM_EPI_ATOMIC_F32: same code, the bulk store becomes a
-// bulk reduce-add) | PLM_EPI_RESID_F32 | PLM_EPI_BF16_SWIGLU | PLM_EPI_BF16_CE
+// bulk reduce-add) | PLM_EPI_RESID_F32 | PLM_EPI_BF16_SWIGLU | PLM_EPI_BF16_CE | PLM_EPI_BF16_GLU_BWD
 template <int EPI, int BN, bool A_K, bool B_K, bool PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__((2 + epi_warps<EPI>()) * 32, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, const GemmParams p) {
   using Cfg = GemmCfg<BN, PAIR, EPI>;
@@ -138,7 +154,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* rope_full = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rope_full + 1);
+  uint64_t* ufull = rope_full + 1;  // [3] GLU backward: the (a, z) chunk pair has landed in its staging tiles
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ufull + 3);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -155,9 +172,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], PAIR ? 2 * GEMM_EPI_WARPS : GEMM_EPI_WARPS);  // PAIR: both CTAs' epilogues drain first
+      mbar_init(&tempty[a], PAIR ? 2 * epi_warps<EPI>() : epi_warps<EPI>());  // PAIR: both CTAs' epilogues drain first
     }
     mbar_init(rope_full, 1);
+    for (int b = 0; b < 3; ++b) mbar_init(&ufull[b], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -297,6 +315,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // measured in round 2: bit-identical, no faster at K = 1024 and 7 % slower at K = 2816 because the extra staging
     // tiles cost two operand stages; these GEMMs are bound by the L2 -> SM operand feed, not by their epilogue.)
     constexpr bool OUT_BF16 = (EPI == PLM_EPI_BF16 || EPI == PLM_EPI_BF16_ROPE || EPI == PLM_EPI_BF16_CE);
+    constexpr int EW = epi_warps<EPI>();
+    const int half = (warp - 2) >> 2;          // EW == 8: which 32-column half of every 64-column chunk this warp takes
     const int q = warp & 3;                    // TMEM lane quarter this warp may read
     const int r_tile = q * 32 + lane;          // row within the tile
     const bool elected = (threadIdx.x == 64);  // warp 2, lane 0 issues the bulk stores
@@ -321,6 +341,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // RoPE, cached table: every epilogue thread tracks (uniformly) which 128-row block's (cos,sin) rows sit in sRope and
     // how many loads have been issued; the elected thread issues the loads — the first here, the others right after the
     // last chunk of the previous tile, i.e. a whole main loop ahead of their use.
+    // GLU backward, elected thread only: the (a, z) chunk loads run one chunk ahead of the chunk being processed
+    int pf_w = cluster_id, pf_c = 0;
+    uint32_t pf_issued = 0;
     const bool rope_cached = (EPI == PLM_EPI_BF16_ROPE) && p.rope_cached && !(PLM_DBG(p) & 1);
     int rope_m = -1;          // row block whose table rows are (being) loaded
     uint32_t rope_loads = 0;  // loads issued so far (parity of rope_full)
@@ -432,13 +455,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         auto emit = [&](const uint32_t(&o)[32], const CUtensorMap* map, int c0) {
           uint8_t* buf = sEpi + (chunk_no & 1) * EPI_BUF_BYTES;
           if (elected) bulk_wait_group_read<1>();
-          named_bar_sync(1, GEMM_EPI_WARPS * 32);
+          named_bar_sync(1, EW * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             *reinterpret_cast<uint4*>(buf + own_off + ((i ^ own_sw) << 4)) =
                 make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
           fence_proxy_async_smem();
-          named_bar_sync(1, GEMM_EPI_WARPS * 32);
+          named_bar_sync(1, EW * 32);
           if (elected && !(PLM_DBG(p) & 2)) {
             tma_store_2d(map, buf, c0, r0);
             bulk_commit_group();
@@ -474,16 +497,96 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           emit(oa, &tmC2, gate_col0 + j * 64);
         }
+      } else if constexpr (EPI == PLM_EPI_BF16_GLU_BWD) {
+        // fc2's input-gradient GEMM fused with the GLU backward (models/components.py:55-56): the accumulator tile is
+        // dg = d(silu(a) z); per 64-column chunk the matching a and z tiles of u = [a | z] are TMA-loaded into a staging
+        // pair (three pairs in rotation) one chunk ahead, each thread turns its row IN PLACE into da = dg z (s + a s (1 - s)) and dz = dg a s
+        // (s = sigmoid(a) = 0.5 tanh(a / 2) + 0.5: one MUFU op per element; packed f32x2 arithmetic), and the pair
+        // leaves through two TMA stores into du = [da | dz].  dg itself is never written.
+        constexpr int NCH = BN / 64;
+#pragma unroll 1
+        for (int c = 0; c < NCH; ++c) {
+          constexpr uint32_t NP = Cfg::GLUB_PAIRS;
+          const uint32_t pi = chunk_no % NP;
+          uint8_t* aBuf = sEpi + pi * (2 * EPI_BUF_BYTES);
+          uint8_t* zBuf = aBuf + EPI_BUF_BYTES;
+          if (elected) {
+            // load #L reuses the pair chunk L - 3 was stored from; at chunk n the stores 0..n-1 are committed and
+            // L <= n + 1, so "all but the most recent group have finished reading" frees it without a stall (with two
+            // pairs the store issued a moment ago had to drain first: 108.7 us per launch at the 420M shape)
+            while (pf_issued <= chunk_no + 1 && pf_w < total) {
+              if (pf_issued >= NP) bulk_wait_group_read<1>();
+              int m2, n2, k0, k1;
+              decode_work<CL>(p, pf_w, rank, m2, n2, k0, k1);
+              const uint32_t b2 = pf_issued % NP;
+              uint8_t* dst = sEpi + b2 * (2 * EPI_BUF_BYTES);
+              mbar_arrive_expect_tx(&ufull[b2], 2 * EPI_BUF_BYTES);
+              tma_load_2d(dst, &tmC2, &ufull[b2], n2 * BN + pf_c * 64, m2 * BM);
+              tma_load_2d(dst + EPI_BUF_BYTES, &tmC2, &ufull[b2], p.glu_F + n2 * BN + pf_c * 64, m2 * BM);
+              ++pf_issued;
+              if (++pf_c == NCH) {
+                pf_c = 0;
+                pf_w += num_clusters;
+              }
+            }
+          }
+          mbar_wait(&ufull[pi], (chunk_no / NP) & 1);
+          {
+            const int h = half;  // eight epilogue warps: this warp's 32-column half of the chunk
+            uint32_t r[32];
+            tmem_ld32(t_row + c * 64 + h * 32, r);
+            tmem_ld_wait();
+            if (c == NCH - 1) release_accumulator(a);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t off = own_off + (((4 * h + i) ^ own_sw) << 4);
+              const uint4 av = *reinterpret_cast<const uint4*>(aBuf + off);
+              const uint4 zv = *reinterpret_cast<const uint4*>(zBuf + off);
+              const uint32_t aw[4] = {av.x, av.y, av.z, av.w};
+              const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
+              uint32_t da[4], dz[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 a2 = make_float2(bf16_lo(aw[k]), bf16_hi(aw[k]));
+                const float2 z2 = make_float2(bf16_lo(zw[k]), bf16_hi(zw[k]));
+                const float2 g2 = make_float2(__uint_as_float(r[8 * i + 2 * k]), __uint_as_float(r[8 * i + 2 * k + 1]));
+                const float2 half2 = make_float2(0.5f, 0.5f);
+                const float2 ha = __fmul2_rn(a2, half2);
+                const float2 t2 = make_float2(tanh_approx(ha.x), tanh_approx(ha.y));
+                const float2 s2 = __ffma2_rn(t2, half2, half2);                                   // sigmoid(a)
+                const float2 as2 = __fmul2_rn(a2, s2);                                            // silu(a)
+                const float2 oms = __ffma2_rn(s2, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));  // 1 - s
+                const float2 q2 = __ffma2_rn(as2, oms, s2);                                       // s + a s (1 - s)
+                const float2 dz2 = __fmul2_rn(g2, as2);
+                const float2 da2 = __fmul2_rn(__fmul2_rn(g2, z2), q2);
+                da[k] = pack_bf16x2(da2.x, da2.y);
+                dz[k] = pack_bf16x2(dz2.x, dz2.y);
+              }
+              *reinterpret_cast<uint4*>(aBuf + off) = make_uint4(da[0], da[1], da[2], da[3]);
+              *reinterpret_cast<uint4*>(zBuf + off) = make_uint4(dz[0], dz[1], dz[2], dz[3]);
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, EW * 32);
+          if (elected && !(PLM_DBG(p) & 2)) {
+            const int c0 = static_cast<int>(tile_col0) + c * 64;
+            tma_store_2d(&tmC, aBuf, c0, r0);
+            tma_store_2d(&tmC, zBuf, p.glu_F + c0, r0);
+            bulk_commit_group();
+          }
+          ++chunk_no;
+        }
       } else if constexpr (OUT_BF16) {
         const int n_chunks = (n_sub + 1) >> 1;  // 64 bf16 columns per staging row
 #pragma unroll 1
         for (int c = 0; c < n_chunks; ++c) {
           uint8_t* buf = sEpi + (chunk_no & 1) * EPI_BUF_BYTES;
           if (elected) bulk_wait_group_read<1>();  // the store that last read this staging tile has drained it
-          named_bar_sync(1, GEMM_EPI_WARPS * 32);
+          named_bar_sync(1, EW * 32);
           uint32_t o[32];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
+            if (EW == 8 && h != half) continue;  // eight epilogue warps: each takes one 32-column half of the chunk
             const int sc = 2 * c + h;
             if (sc < n_sub) {  // warp-uniform
               const bool rope_on = is_rope && (tile_col0 + sc * 32 < p.rope_cols);
@@ -561,11 +664,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (c == n_chunks - 1) release_accumulator(a);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < 8; ++i) {
+            if (EW == 8 && (i >> 2) != half) continue;  // this warp staged only its half of the row
             *reinterpret_cast<uint4*>(buf + own_off + ((i ^ own_sw) << 4)) =
                 make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+          }
           if constexpr (EPI == PLM_EPI_BF16_CE) {
-            if ((tgt_local >> 6) == c) {  // the row's target column is in this chunk: pick it out of the staged row
+            // the row's target column is in the part of this chunk THIS thread staged: pick it out of the staged row
+            if ((tgt_local >> 6) == c && (EW != 8 || ((tgt_local >> 5) & 1) == half)) {
               const int cc = tgt_local & 63;
               const uint16_t bits =
                   *reinterpret_cast<const uint16_t*>(buf + own_off + (((cc >> 3) ^ own_sw) << 4) + (cc & 7) * 2);
@@ -573,7 +679,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, GEMM_EPI_WARPS * 32);
+          named_bar_sync(1, EW * 32);
           if (elected && !(PLM_DBG(p) & 2) && (EPI != PLM_EPI_BF16_CE || p.ce_store)) {
             tma_store_2d(&tmC, buf, static_cast<int>(tile_col0) + c * 64, r0);
             bulk_commit_group();
@@ -582,7 +688,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         if constexpr (EPI == PLM_EPI_BF16_CE) {
           const int64_t row = row_base + r_tile;
-          if (row < p.M) p.ce_partial[static_cast<int64_t>(n_blk) * p.M + row] = make_float2(ce_m, ce_s);
+          // EW == 8: two threads per row, each with the statistics of its column halves -> two partials per tile
+          const int64_t slot = (EW == 8) ? 2 * static_cast<int64_t>(n_blk) + half : static_cast<int64_t>(n_blk);
+          if (row < p.M) p.ce_partial[slot * p.M + row] = make_float2(ce_m, ce_s);
         }
         if (rope_cached) {  // every thread is past its last read of sRope (the chunk barrier above): fetch the next
                             // rotating tile's rows now, a whole main loop ahead of their use
@@ -598,7 +706,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int sc = 0; sc < n_sub; ++sc) {  // 32 fp32 columns per staging row
           uint8_t* buf = sEpi + (chunk_no & 1) * EPI_BUF_BYTES;
           if (elected) bulk_wait_group_read<1>();
-          named_bar_sync(1, GEMM_EPI_WARPS * 32);
+          named_bar_sync(1, EW * 32);
           if (is_resid) {
             stage_aux(buf, nxt);
             __syncwarp();
@@ -626,7 +734,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             *slot = v;
           }
           fence_proxy_async_smem();
-          named_bar_sync(1, GEMM_EPI_WARPS * 32);
+          named_bar_sync(1, EW * 32);
           if (elected && !(PLM_DBG(p) & 2)) {
             const int c0 = static_cast<int>(tile_col0) + sc * 32;
             if (EPI == PLM_EPI_F32 && p.epilogue == PLM_EPI_ATOMIC_F32)
@@ -671,7 +779,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   if (total < clusters) clusters = total;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * CL);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3((2 + epi_warps<EPI>()) * 32);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -712,6 +820,18 @@ int gemm_launch_epi(bool a_k, bool b_k, GemmTile tile, const CUtensorMap& tmA, c
     if (a_k && !b_k) { PLM_GEMM_TILES_(EPI_, true, false) }                                                        \
     if (!a_k && b_k) { PLM_GEMM_TILES_(EPI_, false, true) }                                                        \
     PLM_GEMM_TILES_(EPI_, false, false)                                                                            \
+  }
+
+// fused backward kind: A K-major (the incoming gradient), B MN-major (the weight read in place), 256-wide tiles only
+#define PLM_DEFINE_GEMM_EPI_DGRAD(EPI_)                                                                            \
+  template <>                                                                                                      \
+  int gemm_launch_epi<EPI_>(bool a_k, bool b_k, GemmTile tile, const CUtensorMap& tmA, const CUtensorMap& tmB,     \
+                            const CUtensorMap& tmC, const CUtensorMap& tmC2, const GemmParams& p,                  \
+                            cudaStream_t stream) {                                                                 \
+    if (!(a_k && !b_k) || tile.bn != 256)                                                                          \
+      return fail(PLM_ERR_UNSUPPORTED, "gemm: this fused epilogue needs a K-major A, an MN-major B and N %% 256 == 0"); \
+    if (tile.pair) return launch_gemm<EPI_, 256, true, false, true>(tmA, tmB, tmC, tmC2, p, stream);               \
+    return launch_gemm<EPI_, 256, true, false, false>(tmA, tmB, tmC, tmC2, p, stream);                             \
   }
 
 #define PLM_DEFINE_GEMM_EPI_FORWARD(EPI_)                                                                          \

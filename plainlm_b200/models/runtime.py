@@ -207,6 +207,8 @@ class TrainRuntime:
     self.G = {n: gr(n) for n in p}   # fp32 grad views
     self.P = {n: p[n].data for n in p}
     self.L = L
+    # GLU: fuse d(silu(a) z) into fc2's input-gradient GEMM (PLM_FUSE_GLU_BWD=0: GEMM + plm_swiglu_bwd, for A/B runs)
+    self.fuse_glu_bwd = os.environ.get('PLM_FUSE_GLU_BWD', '1') != '0' and model.hidden_dim % 256 == 0
     _RUNTIMES.add(self)
 
   def release_graphs(self):
@@ -408,13 +410,21 @@ class TrainRuntime:
     for l in reversed(range(L)):
       pre = f'layers.{l}.'
       # ---- MLP branch: x[l+1] = x_mid + fc2(silu(a) * z)
-      self._dgrad(dx_b, pre + 'mlp.fc2.weight', ws.dg)
-      self._wgrad(dx_b, ws.g[l], pre + 'mlp.fc2.weight', f'dx_b{flip}')
-      self._release('du')
-      if self.act_kind is None:
-        ops.swiglu_bwd(ws.dg, ws.u[l], ws.du)
+      if self.act_kind is None and self.fuse_glu_bwd:
+        # fc2's input-gradient GEMM with the GLU backward in its epilogue: du = [da | dz] straight from the accumulator
+        # tile and the saved u = [a | z]; dg is never materialised
+        self._release('du')
+        ops.gemm(dx_b, self.W[pre + 'mlp.fc2.weight'], ws.du, a_kmajor=True, b_kmajor=False,
+                 epilogue=_lib.EPI_BF16_GLU_BWD, out2=ws.u[l])
+        self._wgrad(dx_b, ws.g[l], pre + 'mlp.fc2.weight', f'dx_b{flip}')
       else:
-        ops.act_bwd(ws.dg, ws.u[l], ws.du, self.act_kind)
+        self._dgrad(dx_b, pre + 'mlp.fc2.weight', ws.dg)
+        self._wgrad(dx_b, ws.g[l], pre + 'mlp.fc2.weight', f'dx_b{flip}')
+        self._release('du')
+        if self.act_kind is None:
+          ops.swiglu_bwd(ws.dg, ws.u[l], ws.du)
+        else:
+          ops.act_bwd(ws.dg, ws.u[l], ws.du, self.act_kind)
       self._dgrad(ws.du, pre + 'mlp.fc1.weight', ws.dh)
       self._wgrad(ws.du, ws.h2[l], pre + 'mlp.fc1.weight', 'du')
       dx_b = next_dxb()

@@ -46,9 +46,11 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_BF16, res
   lda, ldb, ldc = _rowmajor_ld(a, 'a'), _rowmajor_ld(b, 'b'), _rowmajor_ld(out, 'out')
   M, K = (a.shape[0], a.shape[1]) if a_kmajor else (a.shape[1], a.shape[0])
   N, Kb = (b.shape[0], b.shape[1]) if b_kmajor else (b.shape[1], b.shape[0])
-  if K != Kb or out.shape[0] != M or out.shape[1] != N:
+  n_out = 2 * N if epilogue == _lib.EPI_BF16_GLU_BWD else N  # GLU backward writes du = [da | dz]
+  if K != Kb or out.shape[0] != M or out.shape[1] != n_out:
     raise ValueError(f'plainlm_b200.gemm: shape mismatch a={tuple(a.shape)} b={tuple(b.shape)} out={tuple(out.shape)}')
-  out_dtype = bf16 if epilogue in (_lib.EPI_BF16, _lib.EPI_BF16_ROPE, _lib.EPI_BF16_SWIGLU, _lib.EPI_BF16_CE) else f32
+  out_dtype = bf16 if epilogue in (_lib.EPI_BF16, _lib.EPI_BF16_ROPE, _lib.EPI_BF16_SWIGLU, _lib.EPI_BF16_CE,
+                                   _lib.EPI_BF16_GLU_BWD) else f32
   args = GemmArgs()
   args.A, args.B, args.C = _ptr(a, bf16, 'a'), _ptr(b, bf16, 'b'), _ptr(out, out_dtype, 'out')
   if residual is not None:
@@ -64,6 +66,10 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_BF16, res
   if epilogue == _lib.EPI_BF16_SWIGLU:
     if out2 is None or out2.shape[0] != M or out2.shape[1] * 2 != N:
       raise ValueError('plainlm_b200.gemm: the SwiGLU epilogue needs out2 of shape [M, N/2]')
+    args.C2, args.ldc2 = _ptr(out2, bf16, 'out2'), _rowmajor_ld(out2, 'out2')
+  if epilogue == _lib.EPI_BF16_GLU_BWD:  # out2 = the saved fc1 output u = [a | z] (an INPUT of this epilogue)
+    if out2 is None or tuple(out2.shape) != (M, 2 * N):
+      raise ValueError('plainlm_b200.gemm: the GLU-backward epilogue needs out2 = u of shape [M, 2N]')
     args.C2, args.ldc2 = _ptr(out2, bf16, 'out2'), _rowmajor_ld(out2, 'out2')
   check(lib.plm_gemm_bf16(ctypes.byref(args), _stream()), 'plm_gemm_bf16')
   return out

@@ -100,6 +100,32 @@ def test_gemm_swiglu_epilogue(M, F, K):
   assert_close(h, torch.nn.functional.silu(ub[:, :F]) * ub[:, F:], BF16_RTOL, what='h')
 
 
+@pytest.mark.parametrize('M,F,K', [(128, 256, 64), (328, 512, 200), (2048, 2816, 1024)])
+def test_gemm_glu_backward_epilogue(M, F, K):
+  """fc2's input-gradient GEMM with the GLU backward fused into its epilogue (PLM_EPI_BF16_GLU_BWD) against autograd of
+  silu(a) * z through the fp32 product of the same bf16 operands, and against the unfused pair GEMM -> plm_swiglu_bwd."""
+  ops, _lib = _ops()
+  g = torch.Generator().manual_seed(M + F)
+  dy = (torch.randn(M, K, generator=g) * 0.5).to(bf16)          # gradient arriving at fc2's output  [M, d]
+  w2 = (torch.randn(K, F, generator=g) * (1.0 / K ** 0.5)).to(bf16)  # fc2.weight [d, F]: read in place as an MN-major B
+  u = (torch.randn(M, 2 * F, generator=g) * 1.5).to(bf16)        # saved fc1 output [a | z]
+  uf = u.float().requires_grad_(True)
+  a, z = uf[:, :F], uf[:, F:]
+  h = torch.nn.functional.silu(a) * z
+  dg_ref = dy.float() @ w2.float()
+  h.backward(dg_ref)
+  du = torch.full((M, 2 * F), float('nan'), device=DEV, dtype=bf16)
+  ops.gemm(dy.to(DEV), w2.to(DEV), du, a_kmajor=True, b_kmajor=False, epilogue=_lib.EPI_BF16_GLU_BWD, out2=u.to(DEV))
+  assert_close(du, uf.grad, BF16_RTOL, what='fused GLU backward')
+  dg = torch.empty(M, F, device=DEV, dtype=bf16)
+  du2 = torch.empty(M, 2 * F, device=DEV, dtype=bf16)
+  ops.gemm(dy.to(DEV), w2.to(DEV), dg, a_kmajor=True, b_kmajor=False)
+  ops.swiglu_bwd(dg, u.to(DEV), du2)
+  assert_close(du, du2, BF16_RTOL, what='fused vs unfused GLU backward')
+  with pytest.raises(Exception):  # K-major B is not instantiated for this kind
+    ops.gemm(dy.to(DEV), w2.t().contiguous().to(DEV), du, epilogue=_lib.EPI_BF16_GLU_BWD, out2=u.to(DEV))
+
+
 def test_gemm_lm_head_shape_sampled():
   """Full LM-head shape of the 420M config (16384 x 50280 x 1024): spot-check entries against fp64 dot products and
   the ragged vocabulary tail (50280 = 196*256 + 104)."""

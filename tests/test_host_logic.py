@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol():
   for n in names:
     assert hasattr(lib, n), f'{n} declared in include/plainlm_b200.h but not exported'
   assert sorted(_lib.SIGNATURES) == names, 'python binding and header disagree on the function set'
-  assert _lib.load().plm_abi_version() == 4
+  assert _lib.load().plm_abi_version() == 5
 
 
 def test_graft_entry_build_passes():

@@ -658,6 +658,39 @@ def case_lmhead_perf():
   return out
 
 
+def case_glu_bwd_perf():
+  """fc2 input-gradient GEMM + GLU backward at the 420M shape: unfused (GEMM -> plm_swiglu_bwd) vs fused epilogue."""
+  import torch
+  from plainlm_b200 import ops, _lib
+
+  dev = 'cuda'
+  M, d, F = 16384, 1024, 2816
+  bf = torch.bfloat16
+  dy = torch.randn(M, d, device=dev).to(bf)
+  w2 = (torch.randn(d, F, device=dev) * 0.03).to(bf)
+  u = torch.randn(M, 2 * F, device=dev).to(bf)
+  dg = torch.empty(M, F, device=dev, dtype=bf)
+  du = torch.empty(M, 2 * F, device=dev, dtype=bf)
+  du2 = torch.empty(M, 2 * F, device=dev, dtype=bf)
+  fl = 2.0 * M * d * F
+
+  def unfused():
+    ops.gemm(dy, w2, dg, a_kmajor=True, b_kmajor=False)
+    ops.swiglu_bwd(dg, u, du)
+
+  fused = lambda: ops.gemm(dy, w2, du2, a_kmajor=True, b_kmajor=False, epilogue=_lib.EPI_BF16_GLU_BWD, out2=u)  # noqa: E731
+  unfused()
+  fused()
+  torch.cuda.synchronize()
+  err = float((du.float() - du2.float()).abs().max() / du.float().abs().max())
+  out = [{'case': 'fused vs unfused rel err', 'rel_to_max': err, 'nan': bool(torch.isnan(du2).any())}]
+  for name, fn in (('dgrad gemm only', lambda: ops.gemm(dy, w2, dg, a_kmajor=True, b_kmajor=False)),
+                   ('swiglu_bwd only', lambda: ops.swiglu_bwd(dg, u, du)), ('unfused', unfused), ('fused', fused)):
+    ms = _time(fn, 20)
+    out.append({'case': name, 'us': round(ms * 1e3, 1), 'gemm_tflops': round(fl / ms / 1e9, 0)})
+  return out
+
+
 def case_attn_perf():
   import torch
   from plainlm_b200 import ops
@@ -768,6 +801,7 @@ CASES['gemm_perf'] = case_gemm_perf
 CASES['lmhead_ce'] = case_lmhead_ce
 CASES['lmhead_ce_ragged'] = lambda: case_lmhead_ce(333, 50280, 64)
 CASES['lmhead_perf'] = case_lmhead_perf
+CASES['glu_bwd_perf'] = case_glu_bwd_perf
 CASES['attn_perf'] = case_attn_perf
 CASES['bw_perf'] = case_bw_perf
 CASES['gemm_epi_perf'] = case_gemm_epi_perf
