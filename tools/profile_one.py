@@ -42,6 +42,16 @@ elif which == 'gemm':
     ops.gemm(g, w2, xo, epilogue=_lib.EPI_RESID_F32, residual=res)                          # fc2 fwd + residual
     ops.gemm(du, w1, dx, a_kmajor=True, b_kmajor=False)                                     # dgrad (K,MN)
     ops.gemm(du, x, dw, a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ATOMIC_F32, splits=0)  # wgrad (MN,MN)
+elif which == 'glu_bwd':
+  dy = torch.randn(M, d, device=dev).to(bf)
+  w2 = (torch.randn(d, F, device=dev) * 0.03).to(bf)
+  u = torch.randn(M, 2 * F, device=dev).to(bf)
+  dg = torch.empty(M, F, device=dev, dtype=bf)
+  du = torch.empty(M, 2 * F, device=dev, dtype=bf)
+  for _ in range(2):
+    ops.gemm(dy, w2, du, a_kmajor=True, b_kmajor=False, epilogue=_lib.EPI_BF16_GLU_BWD, out2=u)  # fused
+    ops.gemm(dy, w2, dg, a_kmajor=True, b_kmajor=False)                                          # the plain dgrad GEMM
+    ops.swiglu_bwd(dg, u, du)                                                                    # ... and its GLU backward
 elif which == 'lmhead':
   V = 50280
   h = torch.randn(M, d, device=dev).to(bf)
