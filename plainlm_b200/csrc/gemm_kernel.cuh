@@ -1,12 +1,15 @@
 // tcgen05 GEMM kernel for every nn.Linear of the plainLM train step (models/transformer.py:42,67,114;
 // models/components.py:55-56) — forward, dgrad and wgrad — replacing the cuBLASLt calls PyTorch makes under autocast.
 //
-// One persistent CTA per SM, 192 threads; launched as 2-CTA clusters whenever there is more than one M block:
+// One persistent CTA per SM, 192 threads (320 for the GLU-backward kind: eight epilogue warps); launched as 2-CTA
+// clusters whenever there is more than one M block:
 //   warp 0      TMA producer   (cp.async.bulk.tensor, 128B-swizzled boxes, STAGES-deep mbarrier ring)
 //   warp 1      MMA issuer     (tcgen05.mma kind::f16, bf16 x bf16 -> fp32 in TMEM; owns TMEM alloc/dealloc).  In PAIR
 //               mode the leader CTA issues ONE tcgen05.mma.cta_group::2 (M = 256) per K-step for both CTAs.
 //   warps 2..5  epilogue       (tcgen05.ld 32x32b, one accumulator row per thread; fused math; 128B-swizzled smem staging
-//               tile; one TMA bulk store / reduce-add per 128-byte-wide column chunk)
+//               tile; one TMA bulk store / reduce-add per 128-byte-wide column chunk).  Kinds: plain bf16 / fp32 / fp32
+//               reduce-add, RoPE (table rows cached in smem through TMA), fp32 residual, SwiGLU (fc1), cross-entropy
+//               statistics (LM head), GLU backward (fc2 dgrad; its a / z operand tiles arrive through TMA too).
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the main loop of
 // tile i+1.  Tile = 128 x BN x 64 per CTA with BN in {128, 256}.  Operands may be K-major or MN-major (UMMA descriptor +
 // instruction-descriptor major bits), which is what lets dgrad and wgrad read activations/weights in place.
