@@ -315,20 +315,26 @@ def test_engine_driven_by_pinned_dataloader_with_workers():
   mc = dict(vocab_size=256, d_model=128, n_layers=2, n_heads=2, seq_len=64, expand='8/3', mlp_class='glu',
             tie_embeddings=False, model='transformer')
   ds = _Rows(48, 64, 256)
+  from plainlm_b200.data_utils import PrefetchLoader
+
   losses = []
-  for use_loader in (True, False):
+  for use_loader in (True, 'prefetch', False):
     model, _ = construct_model(_cfg(**mc))
     model.load_state_dict(orc.init_params(256, 128, 2, 2, seed=4), strict=True)
     eng = TorchEngine(model, _cfg(**_engine_cfg(seq_len=64, grad_accumulation_steps=2)), DEV, None, None)
     if use_loader:
       loader = torch.utils.data.DataLoader(ds, batch_size=4, shuffle=False, num_workers=2, pin_memory=True,
                                            prefetch_factor=2)
+      if use_loader == 'prefetch':  # N1: background thread stages the next batches on the device (side stream + event)
+        loader = PrefetchLoader(loader, DEV, depth=2)
+        assert len(loader) == 12
       cur = [eng.step(batch).item() for batch in loader]
     else:
       cur = [eng.step({'input_ids': ds.data[i : i + 4]}).item() for i in range(0, 48, 4)]
     eng.check_nan(wait=True)
     losses.append(cur)
   # same rows, same weights: equal up to the order of the fp32 reduce-adds (wgrad split-K, dQ), which is not fixed
-  assert len(losses[0]) == len(losses[1]) == 12
-  for a, b in zip(*losses):
+  assert len(losses[0]) == len(losses[1]) == len(losses[2]) == 12
+  for a, p_, b in zip(*losses):
     assert abs(a - b) <= 1e-4 * abs(b), losses
+    assert abs(p_ - b) <= 1e-4 * abs(b), losses

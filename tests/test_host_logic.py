@@ -250,3 +250,50 @@ def test_other_schedules():
   assert lc.get_lr(10) == 1.0 and abs(lc.get_lr(15)) < 1e-12
   lc.load_state_dict({'iter': 7, 'lr_max': 99})
   assert lc.iter == 7 and lc.lr_max == 1.0
+
+
+def test_prefetch_loader_keeps_order_length_and_errors():
+  """PrefetchLoader (N1): same batches in the same order as the wrapped loader, `len` preserved, bounded look-ahead,
+  loader exceptions re-raised in the consumer.  The device copy is injected (identity) so this runs without a GPU."""
+  import threading
+
+  from plainlm_b200.data_utils import PrefetchLoader
+
+  class Ready:
+    def wait(self):
+      pass
+
+  pulled = []
+
+  class Loader:
+    def __init__(self, n, fail_at=None):
+      self.n, self.fail_at = n, fail_at
+
+    def __len__(self):
+      return self.n
+
+    def __iter__(self):
+      for i in range(self.n):
+        if i == self.fail_at:
+          raise RuntimeError('loader broke')
+        pulled.append(i)
+        yield {'input_ids': torch.full((2, 5), i), 'docs_lengths': [[5], [2, 3]]}
+
+  pl = PrefetchLoader(Loader(7), 'cpu', depth=2, to_device=lambda t: (t, Ready()))
+  assert len(pl) == 7
+  seen = []
+  for k, b in enumerate(pl):
+    seen.append(int(b['input_ids'][0, 0]))
+    assert b['docs_lengths'] == [[5], [2, 3]]
+    assert len(pulled) <= k + 1 + 2 + 1  # never more than depth (+1 in flight) ahead of the consumer
+  assert seen == list(range(7))
+  with pytest.raises(RuntimeError, match='loader broke'):
+    for _ in PrefetchLoader(Loader(5, fail_at=3), 'cpu', to_device=lambda t: (t, Ready())):
+      pass
+  # abandoning the iteration early stops the worker thread
+  it = iter(PrefetchLoader(Loader(100), 'cpu', to_device=lambda t: (t, Ready())))
+  next(it)
+  it.close()
+  import time
+  time.sleep(0.5)
+  assert not any(t.name == 'plm-prefetch' and t.is_alive() for t in threading.enumerate())
