@@ -297,3 +297,25 @@ def test_prefetch_loader_keeps_order_length_and_errors():
   import time
   time.sleep(0.5)
   assert not any(t.name == 'plm-prefetch' and t.is_alive() for t in threading.enumerate())
+
+
+def test_binding_constants_match_the_header():
+  """The ctypes side mirrors the header by hand: epilogue kinds, ABI version, activation kinds and the gemm-args struct
+  (field order and count) must agree with include/plainlm_b200.h."""
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  hdr = open(os.path.join(root, 'include', 'plainlm_b200.h')).read()
+  defines = {m.group(1): int(m.group(2)) for m in re.finditer(r'#define\s+(PLM_[A-Z0-9_]+)\s+\(?(-?\d+)\)?', hdr)}
+  for name in ('BF16', 'BF16_ROPE', 'F32', 'RESID_F32', 'ATOMIC_F32', 'BF16_SWIGLU', 'BF16_CE', 'BF16_GLU_BWD'):
+    assert getattr(_lib, 'EPI_' + name) == defines['PLM_EPI_' + name], name
+  assert _lib.load().plm_abi_version() == defines['PLM_ABI_VERSION']
+  assert _lib.SUMSQ_WORKSPACE == defines['PLM_SUMSQ_WORKSPACE']
+  assert (_lib.ACT_SILU, _lib.ACT_RELU2) == (defines['PLM_ACT_SILU'], defines['PLM_ACT_RELU2'])
+  body = re.search(r'typedef struct plm_gemm_args \{(.*?)\} plm_gemm_args;', hdr, re.S).group(1)
+  body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+  fields = []
+  for decl in body.split(';'):
+    decl = decl.strip()
+    if decl:
+      fields += [f.strip().lstrip('*').strip() for f in decl.split(',')]
+  fields = [f.split()[-1].lstrip('*') for f in fields]
+  assert fields == [n for n, _ in _lib.GemmArgs._fields_], (fields, [n for n, _ in _lib.GemmArgs._fields_])
